@@ -1,0 +1,462 @@
+"""
+``HiC3DeFDR``: drop-in for the reference class on the ``run_to_qvalues`` path.
+
+Same constructor kwargs, ``<outdir>/pickle`` and ``HiC3DeFDR.load``
+(hic3defdr/analysis/constructor.py:62-86, analysis/core.py:15-33), same step
+methods and kwargs (analysis/analysis.py:28-364), same per-chromosome ``.npy``
+outputs (analysis/core.py:62-253; shapes and dtypes in DESIGN.md).  The
+arithmetic of every step runs in libh3d (hand-written sm_100a CUDA,
+include/h3d.h); this module only parses inputs, owns the device buffers
+(torch tensors) and writes the files.  There is no CPU fallback.
+
+Differences a caller can observe (all documented in DESIGN.md):
+  * ``n_threads`` is accepted for signature compatibility; it sizes the host
+    I/O thread pool, the compute is on the GPU;
+  * results of a step are also kept on the device (``self._cache``) so that
+    the next step of ``run_to_qvalues`` does not re-read them from disk; every
+    step still works from the files alone in a fresh process;
+  * with ``torch.distributed`` initialised (one process per GPU), chromosomes
+    are sharded across ranks (hic3defdr_b200/dist.py).
+"""
+import json
+import os
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+import dill as pickle
+import numpy as np
+import pandas as pd
+import scipy.sparse as sparse
+import torch
+
+from hic3defdr_b200 import ops
+from hic3defdr_b200 import dist as hdist
+from hic3defdr_b200.trend import lowess_fit, weighted_lowess_fit
+
+
+def eprint(*args, **kwargs):
+    """stderr printing with ``skip=`` (hic3defdr/util/printing.py:5-19)."""
+    if not kwargs.pop('skip', False):
+        print(*args, file=sys.stderr, **kwargs)
+
+
+def check_outdir(path):
+    """lib5c.util.system.check_outdir as used at constructor.py:84."""
+    d = os.path.dirname(path)
+    if d and not os.path.exists(d):
+        print('creating directory %s' % d)
+        os.makedirs(d, exist_ok=True)
+
+
+def load_clusters(infile):
+    """hic3defdr/util/clusters.py:177-193."""
+    with open(infile, 'r') as handle:
+        return [set(tuple(e) for e in cluster) for cluster in json.load(handle)]
+
+
+def _loadtxt(path):
+    try:
+        return pd.read_csv(path, header=None, sep=r'\s+', comment='#',
+                           dtype=np.float64).values[:, 0]
+    except Exception:
+        return np.loadtxt(path)
+
+
+class HiC3DeFDR(object):
+    """See ``hic3defdr.analysis.constructor.HiC3DeFDR`` for the attributes."""
+
+    def __init__(self, raw_npz_patterns, bias_patterns, chroms, design, outdir,
+                 dist_thresh_min=4, dist_thresh_max=200, bias_thresh=0.1,
+                 mean_thresh=1.0, loop_patterns=None, res=None):
+        self.raw_npz_patterns = raw_npz_patterns
+        self.bias_patterns = bias_patterns
+        self.chroms = chroms
+        if type(design) == str:
+            self.design = pd.read_csv(design, index_col=0)
+        else:
+            self.design = design
+        self.outdir = outdir
+        self.dist_thresh_min = dist_thresh_min
+        self.dist_thresh_max = dist_thresh_max
+        self.bias_thresh = bias_thresh
+        self.mean_thresh = mean_thresh
+        self.loop_patterns = loop_patterns
+        self.res = res
+        state = self.__dict__.copy()
+        del state['outdir']
+        if hdist.rank() == 0:
+            check_outdir(self.picklefile)
+            with open(self.picklefile, 'wb') as handle:
+                pickle.dump(state, handle, -1)
+        hdist.barrier()
+        self._cache = {}
+        self.timings = {}
+
+    # ---------------------------------------------------------------- core
+    @property
+    def picklefile(self):
+        return '%s/pickle' % self.outdir
+
+    @classmethod
+    def load(cls, outdir):
+        with open('%s/pickle' % outdir, 'rb') as handle:
+            return cls(outdir=outdir, **pickle.load(handle))
+
+    def _design(self):
+        return np.asarray(self.design.values).astype(bool)
+
+    def load_bias(self, chrom):
+        """analysis/core.py:35-60; returns a numpy (n_bins, n_reps) matrix."""
+        return self._bias_device(chrom).cpu().numpy()
+
+    def _bias_device(self, chrom):
+        c = self._cache.setdefault(chrom, {})
+        if 'bias' not in c:
+            raw = np.array([_loadtxt(p.replace('<chrom>', chrom))
+                            for p in self.bias_patterns]).T
+            c['bias'] = ops.filter_bias(np.ascontiguousarray(raw),
+                                        self.bias_thresh)
+        return c['bias']
+
+    def load_data(self, name, chrom=None, idx=None, rep=None, cond=None,
+                  coo=False):
+        """analysis/core.py:62-195 (same semantics, numpy in / out)."""
+        if name == 'loop_idx' and self.loop_patterns is None and idx is None \
+                and chrom != 'all':
+            disp_idx = self.load_data('disp_idx', chrom)
+            return np.ones(disp_idx.sum(), dtype=bool)
+        col_idx = self.design.index.tolist().index(rep) if rep is not None \
+            else self.design.columns.tolist().index(cond) \
+            if cond is not None else None
+        if coo:
+            if chrom == 'all' or idx is not None:
+                raise ValueError("cannot pass coo=True with chrom='all' or idx")
+            if name in ['row', 'col', 'bias', 'cov_per_bin', 'disp_per_bin']:
+                raise ValueError('data with name %s cannot be loaded as COO'
+                                 % name)
+            if name in ['raw', 'size_factors', 'scaled', 'disp_idx']:
+                row = self.load_data('row', chrom)
+                col = self.load_data('col', chrom)
+            elif name in ['loop_idx', 'disp', 'mu_hat_null', 'mu_hat_alt',
+                          'llr', 'pvalues']:
+                disp_idx = self.load_data('disp_idx', chrom)
+                row = self.load_data('row', chrom, idx=disp_idx)
+                col = self.load_data('col', chrom, idx=disp_idx)
+            elif name in ['qvalues']:
+                disp_idx = self.load_data('disp_idx', chrom)
+                loop_idx = self.load_data('loop_idx', chrom)
+                row = self.load_data('row', chrom, idx=(disp_idx, loop_idx))
+                col = self.load_data('col', chrom, idx=(disp_idx, loop_idx))
+            else:
+                raise ValueError('data name %s not recognized' % name)
+            data = self.load_data(name, chrom)
+            if col_idx is not None:
+                return row, col, data[:, col_idx]
+            return row, col, data
+        if type(idx) == tuple:
+            big_idx, small_idx = idx
+            big_idx = big_idx.copy()
+            big_idx[np.where(big_idx)[0][~small_idx]] = False
+            idx = big_idx
+        if chrom is None:
+            fname = '%s/%s.npy' % (self.outdir, name)
+        elif chrom != 'all':
+            fname = '%s/%s_%s.npy' % (self.outdir, name, chrom)
+        else:
+            fname = None
+        if fname is not None:
+            if idx is None:
+                data = np.load(fname)
+                return data[:, col_idx] if col_idx is not None else data
+            data = np.load(fname, mmap_mode='r')
+            return data[idx, col_idx] if col_idx is not None else data[idx]
+        idx_offset, offset, offsets, all_data = 0, 0, [0], []
+        for chrom in self.chroms:
+            fname = '%s/%s_%s.npy' % (self.outdir, name, chrom)
+            if idx is not None:
+                data = np.load(fname, mmap_mode='r')
+                full = data.shape[0]
+                data = data[idx[idx_offset:idx_offset + full]]
+                idx_offset += full
+            else:
+                data = np.load(fname)
+            offset += data.shape[0]
+            offsets.append(offset)
+            all_data.append(data)
+        all_data = np.concatenate(all_data)
+        if col_idx is not None:
+            return all_data[:, col_idx], np.array(offsets)
+        return all_data, np.array(offsets)
+
+    def save_data(self, data, name, chrom=None):
+        """analysis/core.py:197-218."""
+        if isinstance(data, torch.Tensor):
+            data = data.cpu().numpy()
+        if chrom is None:
+            np.save('%s/%s.npy' % (self.outdir, name), data)
+        elif isinstance(chrom, np.ndarray):
+            for i, c in enumerate(self.chroms):
+                self.save_data(data[chrom[i]:chrom[i + 1]], name, c)
+        else:
+            np.save('%s/%s_%s.npy' % (self.outdir, name, chrom), data)
+
+    def load_disp_fn(self, cond):
+        """analysis/core.py:220-237."""
+        with open('%s/disp_fn_%s.pickle' % (self.outdir, cond), 'rb') as h:
+            return pickle.load(h)
+
+    def save_disp_fn(self, cond, disp_fn):
+        """analysis/core.py:239-253."""
+        with open('%s/disp_fn_%s.pickle' % (self.outdir, cond), 'wb') as h:
+            return pickle.dump(disp_fn, h, -1)
+
+    # ------------------------------------------------------------ helpers
+    def _my_chroms(self):
+        return hdist.shard_chroms(self.chroms, self._chrom_weight)
+
+    def _chrom_weight(self, chrom):
+        try:
+            return os.path.getsize(
+                self.raw_npz_patterns[0].replace('<chrom>', chrom))
+        except OSError:
+            return 1
+
+    def _io_threads(self, n_threads):
+        if n_threads is None or n_threads == 0:
+            return 1
+        if n_threads < 0:
+            return max(1, min(os.cpu_count() or 1, 16))
+        return n_threads
+
+    def _save_many(self, items, n_threads=-1):
+        """items: list of (tensor-or-array, name, chrom)."""
+        host = [(d.cpu().numpy() if isinstance(d, torch.Tensor) else d, n, c)
+                for d, n, c in items]
+        with ThreadPoolExecutor(self._io_threads(n_threads)) as ex:
+            list(ex.map(lambda a: self.save_data(*a), host))
+
+    def _chrom_state(self, chrom, names):
+        """device tensors of one chromosome, from the cache or from disk."""
+        c = self._cache.setdefault(chrom, {})
+        for name in names:
+            if name in c:
+                continue
+            if name == 'bias':
+                self._bias_device(chrom)
+            elif name == 'disp_index':
+                di = self._chrom_state(chrom, ['disp_idx'])['disp_idx']
+                c['disp_index'] = ops.mask_to_index(di)
+            else:
+                arr = self.load_data(name, chrom)
+                if arr.dtype == np.bool_:
+                    arr = arr.view(np.uint8)
+                c[name] = ops.dev(arr)
+        return c
+
+    def free_device_cache(self):
+        self._cache = {}
+        torch.cuda.empty_cache()
+
+    # ------------------------------------------------------- prepare_data
+    def prepare_data(self, chrom=None, norm='conditional_mor', n_bins=-1,
+                     n_threads=-1, verbose=True):
+        """analysis/analysis.py:28-133."""
+        if n_bins == -1:
+            n_bins = int(self.dist_thresh_max / 5)
+        if norm not in ops.NORMS:
+            raise KeyError(norm)
+        if chrom is None:
+            for c in self._my_chroms():
+                self.prepare_data(chrom=c, norm=norm, n_bins=n_bins,
+                                  n_threads=n_threads, verbose=False)
+            hdist.barrier()
+            return
+        eprint('preparing data for chrom %s' % chrom)
+        eprint('  loading bias', skip=not verbose)
+        self._cache.pop(chrom, None)
+        bias = self._bias_device(chrom)
+
+        eprint('  computing union pixel set', skip=not verbose)
+        with ThreadPoolExecutor(self._io_threads(n_threads)) as ex:
+            mats = list(ex.map(
+                lambda p: sparse.load_npz(p.replace('<chrom>', chrom)).tocsr(),
+                self.raw_npz_patterns))
+        csr = ops.DeviceCSR(mats)
+        del mats
+        eprint('  loading raw data', skip=not verbose)
+        eprint('  loading balanced data', skip=not verbose)
+        u = ops.union_gather(csr, self.dist_thresh_max, bias)
+        del csr
+        row, col, dist, raw, data = u['row'], u['col'], u['dist'], u['raw'], \
+            u['balanced']
+
+        eprint('  computing size factors', skip=not verbose)
+        table = ops.size_factor_table(data, dist, self.dist_thresh_max, n_bins,
+                                      norm)
+        eprint('  computing disp_idx', skip=not verbose)
+        scaled, size_factors, disp_idx = ops.scale_filter(
+            row, col, data, table, self._design(), self.dist_thresh_max,
+            self.mean_thresh, self.dist_thresh_min)
+        disp_index = ops.mask_to_index(disp_idx)
+        to_save = []
+        if self.loop_patterns:
+            eprint('  making loop_idx', skip=not verbose)
+            loop_pixels = set().union(
+                *sum((load_clusters(pattern.replace('<chrom>', chrom))
+                      for pattern in self.loop_patterns.values()), []))
+            loop_idx = ops.loop_membership(row, col, disp_index, loop_pixels)
+            to_save.append((loop_idx.bool(), 'loop_idx', chrom))
+        eprint('  saving data to disk', skip=not verbose)
+        to_save += [(row, 'row', chrom), (col, 'col', chrom),
+                    (raw, 'raw', chrom),
+                    (size_factors, 'size_factors', chrom),
+                    (scaled, 'scaled', chrom),
+                    (disp_idx.bool(), 'disp_idx', chrom)]
+        self._save_many(to_save, n_threads)
+        c = self._cache.setdefault(chrom, {})
+        c.update(row=row, col=col, raw=raw, size_factors=size_factors,
+                 disp_idx=disp_idx, disp_index=disp_index)
+        if self.loop_patterns:
+            c['loop_idx'] = loop_idx
+
+    # ------------------------------------------------------ estimate_disp
+    def estimate_disp(self, estimator='qcml', frac=None, auto_frac_factor=15.,
+                      weighted_lowess=True, n_threads=-1):
+        """analysis/analysis.py:135-223."""
+        eprint('estimating dispersion')
+        if not isinstance(estimator, str) or estimator not in ops.ESTIMATORS:
+            raise ValueError(
+                "estimator must be one of 'qcml', 'cml', 'mme' on the GPU "
+                "path (python callables cannot run on the device)")
+        lowess_fn = weighted_lowess_fit if weighted_lowess else lowess_fit
+        design = self._design()
+        n_reps, n_conds = design.shape
+        dmax = self.dist_thresh_max
+        eprint('  loading data')
+        mine = self._my_chroms()
+        states = [self._chrom_state(
+            c, ['row', 'col', 'raw', 'size_factors', 'disp_idx', 'disp_index',
+                'bias']) for c in mine]
+        counts = [int(s['disp_index'].numel()) for s in states]
+        offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        n_tot = int(offs[-1])
+        dist_cat = torch.empty(n_tot, dtype=torch.int32, device='cuda')
+        for s, o, n in zip(states, offs[:-1], counts):
+            if s['size_factors'].dim() != 2:
+                raise IndexError(
+                    'estimate_disp needs per-pixel size factors (a '
+                    'conditional norm), as in the reference '
+                    '(analysis/analysis.py:181)')
+            ops.gather_counts_factors(s['row'], s['col'], s['disp_index'],
+                                      None, None, None, None, n_tot, None,
+                                      None, dist_cat[o:o + n])
+        # pool by distance: stable rank keeps (chromosome, row, col) order
+        # inside every distance, the order of ``raw[dist == d]`` in the
+        # reference (analysis/analysis.py:196-197)
+        rank, key_start = ops.stable_rank(dist_cat, dmax + 1) if n_tot else \
+            (dist_cat, torch.zeros(dmax + 2, dtype=torch.int64))
+        x = torch.empty((n_reps, max(n_tot, 1)), dtype=torch.float64,
+                        device='cuda')
+        f = torch.empty_like(x)
+        for s, o, n in zip(states, offs[:-1], counts):
+            ops.gather_counts_factors(s['row'], s['col'], s['disp_index'],
+                                      s['raw'], s['size_factors'], s['bias'],
+                                      rank[o:o + n], x.shape[1], x, f, None)
+        seg_start = key_start.cpu().numpy()
+        # multi-GPU: regroup so that every distance lives on one rank
+        x, f, seg_start, owner = hdist.exchange_by_distance(
+            x, f, seg_start, n_tot)
+        disp_per_dist, stats = ops.estimate_dispersion(
+            x, f, seg_start, design, estimator)
+        disp_per_dist = hdist.merge_disp_per_dist(disp_per_dist, owner)
+        self.timings['qcml_stats'] = stats
+        del x, f
+
+        disp = torch.empty((n_tot, n_conds), dtype=torch.float64,
+                           device='cuda')
+        table = np.full((dmax + 1, n_conds), np.nan)
+        for c, cond in enumerate(self.design.columns):
+            eprint('  estimating dispersion for condition %s' % cond)
+            eprint('  fitting distance vs dispersion relationship')
+            idx = np.isfinite(disp_per_dist[:, c])
+            xs = np.arange(dmax + 1)[idx]
+            ys = disp_per_dist[:, c][idx]
+            lowess_kwargs = {'left_boundary': ys[0]}
+            if frac is not None:
+                lowess_kwargs['frac'] = frac
+            if weighted_lowess:
+                lowess_kwargs['auto_frac_factor'] = auto_frac_factor
+            disp_fn = lowess_fn(xs, ys, **lowess_kwargs)
+            table[:, c] = disp_fn(np.arange(dmax + 1))
+            if hdist.rank() == 0:
+                self.save_disp_fn(cond, disp_fn)
+        if n_tot:
+            disp = ops.gather_table(dist_cat, table)
+        eprint('  saving estimated dispersions to disk')
+        items = []
+        for i, (c, s) in enumerate(zip(mine, states)):
+            d = disp[offs[i]:offs[i + 1]]
+            self._cache[c]['disp'] = d
+            items.append((d, 'disp', c))
+        self._save_many(items, n_threads)
+        if hdist.rank() == 0:
+            self.save_data(disp_per_dist, 'disp_per_dist')
+        hdist.barrier()
+
+    # ---------------------------------------------------------------- lrt
+    def lrt(self, chrom=None, refit_mu=True, n_threads=-1, verbose=True):
+        """analysis/analysis.py:225-284."""
+        if chrom is None:
+            for c in self._my_chroms():
+                self.lrt(chrom=c, refit_mu=refit_mu, n_threads=n_threads,
+                         verbose=False)
+            hdist.barrier()
+            return
+        eprint('running LRT for chrom %s' % chrom)
+        eprint('  loading data', skip=not verbose)
+        s = self._chrom_state(chrom, ['bias', 'size_factors', 'disp_idx',
+                                      'disp_index', 'row', 'col', 'raw',
+                                      'disp'])
+        eprint('  computing LRT results', skip=not verbose)
+        p, llr, mu0, mu1 = ops.lrt_fused(
+            s['row'], s['col'], s['disp_index'], s['raw'], s['size_factors'],
+            s['bias'], s['disp'], self._design(), refit_mu)
+        eprint('  saving results to disk', skip=not verbose)
+        self._save_many([(p, 'pvalues', chrom), (llr, 'llr', chrom),
+                         (mu0, 'mu_hat_null', chrom),
+                         (mu1, 'mu_hat_alt', chrom)], n_threads)
+        s['pvalues'] = p
+
+    # ----------------------------------------------------------------- bh
+    def bh(self):
+        """analysis/analysis.py:286-303."""
+        eprint('applying BH-FDR correction')
+        mine = self._my_chroms()
+        ps = []
+        for c in mine:
+            s = self._chrom_state(c, ['pvalues'])
+            p = s['pvalues']
+            if self.loop_patterns:
+                li = self._chrom_state(c, ['loop_idx'])['loop_idx']
+                p = p[li.bool()]
+            ps.append(p)
+        counts = [int(p.numel()) for p in ps]
+        local = torch.cat(ps) if ps else torch.empty(
+            0, dtype=torch.float64, device='cuda')
+        q = hdist.global_bh(local)
+        offs = np.concatenate([[0], np.cumsum(counts)])
+        self._save_many([(q[offs[i]:offs[i + 1]], 'qvalues', c)
+                         for i, c in enumerate(mine)])
+        hdist.barrier()
+
+    def run_to_qvalues(self, norm='conditional_mor', n_bins_norm=-1,
+                       estimator='qcml', frac=None, auto_frac_factor=15.,
+                       weighted_lowess=True, refit_mu=True, n_threads=-1,
+                       verbose=True):
+        """analysis/analysis.py:305-364."""
+        self.prepare_data(norm=norm, n_bins=n_bins_norm, n_threads=n_threads)
+        self.estimate_disp(
+            estimator=estimator, frac=frac, auto_frac_factor=auto_frac_factor,
+            weighted_lowess=weighted_lowess, n_threads=n_threads)
+        self.lrt(refit_mu=refit_mu, n_threads=n_threads)
+        self.bh()

@@ -1,0 +1,454 @@
+// Per-(distance, condition) dispersion estimation: qCML, CML, MME.
+//
+// Replaces hic3defdr/util/dispersion.py:10-131 (qcml, cml, mme,
+// mme_per_pixel) and hic3defdr/util/scaled_nb.py:186-275 (equalize,
+// q2qnbinom), i.e. the body of the distance loop at
+// hic3defdr/analysis/analysis.py:191-206.
+//
+// The reference runs one scipy optimisation per (distance, condition) bin in
+// a process pool.  Here ALL bins advance in lock step: the pooled pixels sit
+// distance-major in SoA arrays, every launch works on every bin that is in the
+// corresponding phase, and the tiny per-bin control state (qCML fixed point,
+// Brent bracket) lives in device arrays updated by a one-thread-per-bin kernel.
+//   equalize_kernel : per pixel fit_mu + q2q pseudo-data at the bin's current
+//                     dispersion (FP64 special functions; the dominant cost)
+//   nll_kernel      : per-chunk partial sums of the conditional NB
+//                     log-likelihood at the bin's current Brent abscissa
+//   step_kernel     : sums a bin's partials in a fixed order (deterministic),
+//                     advances scipy's bounded Brent state machine, applies
+//                     the qCML stopping rule |delta disp| <= 1e-4
+// FP64-pipe bound: ~44 k FP64 instruction-
+// equivalents per pixel against 16 R_c bytes read + 8 R_c written per sweep.
+#include <vector>
+
+#include "common.cuh"
+
+namespace h3d {
+
+constexpr int kChunk = 1024;        // pixels per partial sum
+constexpr double kQcmlTol = 1e-4;   // dispersion.py:10
+constexpr double kBrentXatol = 1e-5;
+constexpr int kBrentMaxfun = 500;
+constexpr double kDeltaLo = 1e-4, kDeltaHi = 100.0 / 101.0;   // dispersion.py:77
+
+enum : int { ST_EMPTY = 0, ST_NEED_EQ = 1, ST_IN_BRENT = 2, ST_DONE = 3, ST_FAILED = 4 };
+
+struct CondReps {
+    int rep[H3D_MAX_CONDS][H3D_MAX_REPS];   // replicate indices of each condition
+    int n_in[H3D_MAX_CONDS];
+    int pseudo_row[H3D_MAX_CONDS];          // first row of the condition in the pseudo buffer
+    int n_conds;
+};
+
+struct Problem {                 // one (segment, condition)
+    BrentState brent;
+    double disp;
+    long long n_px;
+    int status, outer_iters, nfev_total, pad;
+};
+
+struct Counters { int n_need_eq, n_in_brent, n_failed, n_fit_failed; };
+
+__global__ void init_problems_kernel(Problem* __restrict__ prob, const long long* __restrict__ seg_start,
+                                     int n_seg, int n_conds, int estimator, Counters* cnt) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p == 0) { cnt->n_need_eq = 0; cnt->n_in_brent = 0; cnt->n_failed = 0; cnt->n_fit_failed = 0; }
+    if (p >= n_seg * n_conds) return;
+    const int s = p / n_conds;
+    Problem& q = prob[p];
+    q.n_px = seg_start[s + 1] - seg_start[s];
+    q.outer_iters = 0; q.nfev_total = 0;
+    q.disp = (q.n_px > 0) ? 0.01 : NAN;                 // dispersion.py:33 / analysis.py:205
+    q.status = (q.n_px > 0) ? ST_NEED_EQ : ST_EMPTY;
+    (void)estimator;
+}
+
+// pseudo-data for every pixel of every bin that waits for it.
+// grid = (n_chunks, n_conds); blockDim = 256; chunk -> (segment, first pixel)
+template <int MAXRC>
+__global__ void __launch_bounds__(256)
+equalize_kernel(const double* __restrict__ x, const double* __restrict__ f, long long ld,
+                const int* __restrict__ chunk_seg, const long long* __restrict__ chunk_lo,
+                const long long* __restrict__ seg_start, CondReps cr, int estimator,
+                const Problem* __restrict__ prob, double* __restrict__ pseudo, Counters* cnt) {
+    const int c = blockIdx.y;
+    const int s = chunk_seg[blockIdx.x];
+    const Problem& q = prob[s * cr.n_conds + c];
+    if (q.status != ST_NEED_EQ) return;
+    const double alpha = q.disp;
+    const long long lo = chunk_lo[blockIdx.x];
+    const long long seg_hi = seg_start[s + 1];
+    const long long hi = (lo + kChunk < seg_hi) ? lo + kChunk : seg_hi;
+    const int nr = cr.n_in[c];
+    for (long long i = lo + threadIdx.x; i < hi; i += 256) {
+        double xr[MAXRC], fr[MAXRC], ar[MAXRC];
+        double slog = 0.0;
+#pragma unroll
+        for (int k = 0; k < MAXRC; ++k) {
+            xr[k] = 0.0; fr[k] = 1.0; ar[k] = alpha;
+            if (k < nr) {
+                const int r = cr.rep[c][k];
+                xr[k] = x[(long long)r * ld + i];
+                fr[k] = f[(long long)r * ld + i];
+                slog += log(fr[k]);
+            }
+        }
+        double* out = pseudo + (long long)cr.pseudo_row[c] * ld + i;
+        if (estimator == H3D_EST_CML) {
+            // cml(raw, f): data / f (dispersion.py:67-68, intended semantics)
+#pragma unroll
+            for (int k = 0; k < MAXRC; ++k)
+                if (k < nr) out[(long long)k * ld] = xr[k] / fr[k];
+            continue;
+        }
+        // equalize (scaled_nb.py:207-214)
+        const double f_mean = exp(slog / (double)nr);       // gmean, pseudocount 0
+        int st = 0;
+        const double mu_hat = fit_mu<MAXRC>(xr, fr, ar, (1u << nr) - 1u, &st);
+        if (st) atomicAdd(&cnt->n_fit_failed, 1);
+        double mu_out = mu_hat * f_mean;
+#pragma unroll
+        for (int k = 0; k < MAXRC; ++k) {
+            if (k < nr) {
+                double mu_in = mu_hat * fr[k];
+                // order-dependent clamp shared across replicates (scaled_nb.py:240-242)
+                if (!((mu_in >= 0.25) && (mu_out >= 0.25))) { mu_in = 0.25; mu_out = 0.25; }
+                out[(long long)k * ld] = q2q_one(xr[k], mu_in, mu_out, alpha);
+            }
+        }
+    }
+}
+
+// deterministic block sum: shuffle tree inside warps, then warp 0 adds the 8
+// warp results in index order
+__device__ __forceinline__ double block_sum_256(double v, double* sh) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0) for (int w = 0; w < 8; ++w) t += sh[w];
+    return t;
+}
+
+// conditional NB negative log-likelihood partials (dispersion.py:72-75)
+template <int MAXRC>
+__global__ void __launch_bounds__(256)
+nll_kernel(const double* __restrict__ pseudo, long long ld, const int* __restrict__ chunk_seg,
+           const long long* __restrict__ chunk_lo, const long long* __restrict__ seg_start,
+           CondReps cr, const Problem* __restrict__ prob, double* __restrict__ partial,
+           int n_chunks) {
+    __shared__ double sh[8];
+    const int c = blockIdx.y;
+    const int s = chunk_seg[blockIdx.x];
+    const Problem& q = prob[s * cr.n_conds + c];
+    if (q.status != ST_IN_BRENT) return;
+    const double delta = q.brent.x_eval;
+    const double r = 1.0 / delta - 1.0;
+    const int nr = cr.n_in[c];
+    const double nrr = (double)nr * r;
+    const double cst = lgamma(nrr) - (double)nr * lgamma(r);
+    const long long lo = chunk_lo[blockIdx.x];
+    const long long seg_hi = seg_start[s + 1];
+    const long long hi = (lo + kChunk < seg_hi) ? lo + kChunk : seg_hi;
+    const double* __restrict__ base = pseudo + (long long)cr.pseudo_row[c] * ld;
+    double acc = 0.0;
+    for (long long i = lo + threadIdx.x; i < hi; i += 256) {
+        double z = 0.0, lg = 0.0;
+#pragma unroll
+        for (int k = 0; k < MAXRC; ++k) {
+            if (k < nr) {
+                const double y = base[(long long)k * ld + i];
+                z += y;
+                lg += lgamma(y + r);
+            }
+        }
+        acc += (lg + cst) - lgamma(z + nrr);
+    }
+    const double tot = block_sum_256(acc, sh);
+    if (threadIdx.x == 0) partial[(long long)c * n_chunks + blockIdx.x] = tot;
+}
+
+// MME partials: sum and count of the finite per-pixel estimates
+// (dispersion.py:101-105, 129-131)
+template <int MAXRC>
+__global__ void __launch_bounds__(256)
+mme_kernel(const double* __restrict__ x, const double* __restrict__ f, long long ld,
+           const int* __restrict__ chunk_seg, const long long* __restrict__ chunk_lo,
+           const long long* __restrict__ seg_start, CondReps cr, double* __restrict__ partial,
+           double* __restrict__ partial_cnt, int n_chunks) {
+    __shared__ double sh[8];
+    const int c = blockIdx.y;
+    const int s = chunk_seg[blockIdx.x];
+    const long long lo = chunk_lo[blockIdx.x];
+    const long long seg_hi = seg_start[s + 1];
+    const long long hi = (lo + kChunk < seg_hi) ? lo + kChunk : seg_hi;
+    const int nr = cr.n_in[c];
+    double acc = 0.0, cntv = 0.0;
+    for (long long i = lo + threadIdx.x; i < hi; i += 256) {
+        double v[MAXRC];
+        double m = 0.0;
+#pragma unroll
+        for (int k = 0; k < MAXRC; ++k) {
+            v[k] = 0.0;
+            if (k < nr) {
+                const int r = cr.rep[c][k];
+                v[k] = x[(long long)r * ld + i] / f[(long long)r * ld + i];
+                m += v[k];
+            }
+        }
+        m /= (double)nr;
+        double ss = 0.0;
+#pragma unroll
+        for (int k = 0; k < MAXRC; ++k)
+            if (k < nr) { const double dlt = v[k] - m; ss += dlt * dlt; }
+        const double var = ss / (double)(nr - 1);
+        const double est = (var - m) / (m * m);             // inverse_mvr (scaled_nb.py:68)
+        if (!isnan(est)) { acc += est; cntv += 1.0; }
+    }
+    const double tot = block_sum_256(acc, sh);
+    __syncthreads();
+    const double tc = block_sum_256(cntv, sh);
+    if (threadIdx.x == 0) {
+        partial[(long long)c * n_chunks + blockIdx.x] = tot;
+        partial_cnt[(long long)c * n_chunks + blockIdx.x] = tc;
+    }
+}
+
+// one thread per problem.  mode 0: start a Brent search for bins whose
+// pseudo-data were just (re)computed; mode 1: consume the NLL partials;
+// mode 2: finish MME.
+__global__ void step_kernel(Problem* __restrict__ prob, const int* __restrict__ seg_chunk_start,
+                            const double* __restrict__ partial, const double* __restrict__ partial_cnt,
+                            int n_chunks, int n_seg, int n_conds, int estimator, int mode,
+                            Counters* cnt) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_seg * n_conds) return;
+    const int s = p / n_conds, c = p % n_conds;
+    Problem& q = prob[p];
+    if (mode == 2) {
+        if (q.status == ST_EMPTY) return;
+        double sum = 0.0, n = 0.0;
+        for (int k = seg_chunk_start[s]; k < seg_chunk_start[s + 1]; ++k) {
+            sum += partial[(long long)c * n_chunks + k];
+            n += partial_cnt[(long long)c * n_chunks + k];
+        }
+        q.disp = sum / n;                                   // nanmean
+        q.status = ST_DONE;
+        return;
+    }
+    if (mode == 0) {
+        if (q.status != ST_NEED_EQ) return;
+        brent_begin(q.brent, kDeltaLo, kDeltaHi);
+        q.status = ST_IN_BRENT;
+        atomicAdd(&cnt->n_in_brent, 1);
+        return;
+    }
+    if (q.status != ST_IN_BRENT) return;
+    double sum = 0.0;
+    for (int k = seg_chunk_start[s]; k < seg_chunk_start[s + 1]; ++k)
+        sum += partial[(long long)c * n_chunks + k];
+    const double fu = -sum;
+    const bool more = brent_advance(q.brent, fu, kBrentXatol, kBrentMaxfun);
+    if (more) { atomicAdd(&cnt->n_in_brent, 1); return; }
+    q.nfev_total += q.brent.num;
+    if (q.brent.flag != 0) {                                // assert res.success (dispersion.py:78)
+        q.status = ST_FAILED; q.disp = NAN;
+        atomicAdd(&cnt->n_failed, 1);
+        return;
+    }
+    const double dh = q.brent.xf;
+    const double nd = dh / (1.0 - dh);
+    q.outer_iters += 1;
+    if (estimator == H3D_EST_CML) { q.disp = nd; q.status = ST_DONE; return; }
+    const double dl = fabs(q.disp - nd);                    // dispersion.py:36-42
+    q.disp = nd;
+    if (dl > kQcmlTol) { q.status = ST_NEED_EQ; atomicAdd(&cnt->n_need_eq, 1); }
+    else q.status = ST_DONE;
+}
+
+__global__ void reset_counters_kernel(Counters* cnt) { cnt->n_need_eq = 0; cnt->n_in_brent = 0; }
+
+__global__ void collect_kernel(const Problem* __restrict__ prob, int n, double* __restrict__ disp_out,
+                               long long* __restrict__ stats) {
+    // single block
+    __shared__ long long it_sum, fev_sum, eq_sum;
+    if (threadIdx.x == 0) { it_sum = 0; fev_sum = 0; eq_sum = 0; }
+    __syncthreads();
+    for (int p = threadIdx.x; p < n; p += blockDim.x) {
+        disp_out[p] = prob[p].disp;
+        atomicAdd((unsigned long long*)&it_sum, (unsigned long long)prob[p].outer_iters);
+        atomicAdd((unsigned long long*)&fev_sum, (unsigned long long)prob[p].nfev_total);
+        atomicAdd((unsigned long long*)&eq_sum,
+                  (unsigned long long)((long long)prob[p].outer_iters * prob[p].n_px));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { stats[0] = it_sum; stats[1] = fev_sum; stats[2] = eq_sum; }
+}
+
+}  // namespace h3d
+
+using namespace h3d;
+
+static long long count_chunks(const long long* seg_start_host, int n_seg) {
+    long long n = 0;
+    for (int s = 0; s < n_seg; ++s) n += (seg_start_host[s + 1] - seg_start_host[s] + kChunk - 1) / kChunk;
+    return n;
+}
+
+extern "C" size_t h3d_estimate_dispersion_ws_bytes(long long n_px, int n_seg, int n_reps, int n_conds) {
+    const long long max_chunks = n_px / kChunk + n_seg + 1;
+    size_t b = 0;
+    b += ws_pad((size_t)n_reps * n_conds * n_px * 8);               // pseudo (worst case)
+    b += 2 * ws_pad((size_t)n_conds * max_chunks * 8);               // partials
+    b += ws_pad((size_t)max_chunks * 4) + ws_pad((size_t)max_chunks * 8);
+    b += ws_pad((size_t)(n_seg + 1) * 8) + ws_pad((size_t)(n_seg + 1) * 4);
+    b += ws_pad((size_t)n_seg * n_conds * sizeof(Problem));
+    b += ws_pad((size_t)n_seg * n_conds * 8) + ws_pad(64) + ws_pad(64);
+    return b;
+}
+
+extern "C" int h3d_estimate_dispersion(const double* x, const double* f, long long ld,
+                                       const long long* seg_start_host, int n_seg,
+                                       const unsigned char* design_host, int n_reps, int n_conds,
+                                       int estimator, double* disp_per_dist_host,
+                                       long long* stats_host, void* ws, size_t ws_bytes,
+                                       h3d_stream_t stream) {
+    H3D_REQUIRE(n_reps >= 1 && n_reps <= H3D_MAX_REPS, "n_reps out of range");
+    H3D_REQUIRE(n_conds >= 1 && n_conds <= H3D_MAX_CONDS, "n_conds out of range");
+    H3D_REQUIRE(estimator >= 0 && estimator <= 2, "unknown estimator");
+    H3D_REQUIRE(n_seg >= 1, "no segments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned long long launches_before = h3d_launch_count();
+    CondReps cr;
+    cr.n_conds = n_conds;
+    int rows = 0, max_rc = 0;
+    for (int c = 0; c < H3D_MAX_CONDS; ++c) {
+        cr.n_in[c] = 0; cr.pseudo_row[c] = rows;
+        for (int k = 0; k < H3D_MAX_REPS; ++k) cr.rep[c][k] = 0;
+        if (c >= n_conds) continue;
+        for (int r = 0; r < n_reps; ++r)
+            if (design_host[r * n_conds + c]) cr.rep[c][cr.n_in[c]++] = r;
+        H3D_REQUIRE(cr.n_in[c] >= 1, "condition without replicates");
+        rows += cr.n_in[c];
+        if (cr.n_in[c] > max_rc) max_rc = cr.n_in[c];
+    }
+    const long long n_px = seg_start_host[n_seg] - seg_start_host[0];
+    H3D_REQUIRE(seg_start_host[0] == 0 && n_px <= ld, "segments must start at 0 and fit in ld");
+    const int n_prob = n_seg * n_conds;
+    for (int p = 0; p < n_prob; ++p) disp_per_dist_host[p] = NAN;
+    if (stats_host) for (int k = 0; k < 4; ++k) stats_host[k] = 0;
+    if (n_px == 0) return H3D_OK;
+
+    // chunk tables (host)
+    const long long n_chunks_ll = count_chunks(seg_start_host, n_seg);
+    H3D_REQUIRE(n_chunks_ll < 2147483647LL, "too many chunks");
+    const int n_chunks = (int)n_chunks_ll;
+    std::vector<int> h_chunk_seg(n_chunks), h_seg_chunk_start(n_seg + 1);
+    std::vector<long long> h_chunk_lo(n_chunks);
+    int k = 0;
+    for (int s = 0; s < n_seg; ++s) {
+        h_seg_chunk_start[s] = k;
+        for (long long lo = seg_start_host[s]; lo < seg_start_host[s + 1]; lo += kChunk) {
+            h_chunk_seg[k] = s; h_chunk_lo[k] = lo; ++k;
+        }
+    }
+    h_seg_chunk_start[n_seg] = k;
+
+    Workspace w(ws, ws_bytes);
+    double* pseudo = w.take<double>((size_t)rows * ld);
+    double* partial = w.take<double>((size_t)n_conds * n_chunks);
+    double* partial_cnt = w.take<double>((size_t)n_conds * n_chunks);
+    int* chunk_seg = w.take<int>(n_chunks);
+    long long* chunk_lo = w.take<long long>(n_chunks);
+    long long* seg_start = w.take<long long>(n_seg + 1);
+    int* seg_chunk_start = w.take<int>(n_seg + 1);
+    Problem* prob = w.take<Problem>(n_prob);
+    double* disp_dev = w.take<double>(n_prob);
+    Counters* cnt = w.take<Counters>(1);
+    long long* stats_dev = w.take<long long>(4);
+    if (!pseudo || !partial || !partial_cnt || !chunk_seg || !chunk_lo || !seg_start ||
+        !seg_chunk_start || !prob || !disp_dev || !cnt || !stats_dev) {
+        set_error("estimate_dispersion workspace too small (%zu bytes given)", ws_bytes);
+        return H3D_ERR_WORKSPACE;
+    }
+    H3D_CHECK(cudaMemcpyAsync(chunk_seg, h_chunk_seg.data(), (size_t)n_chunks * 4, cudaMemcpyHostToDevice, st));
+    H3D_CHECK(cudaMemcpyAsync(chunk_lo, h_chunk_lo.data(), (size_t)n_chunks * 8, cudaMemcpyHostToDevice, st));
+    H3D_CHECK(cudaMemcpyAsync(seg_start, seg_start_host, (size_t)(n_seg + 1) * 8, cudaMemcpyHostToDevice, st));
+    H3D_CHECK(cudaMemcpyAsync(seg_chunk_start, h_seg_chunk_start.data(), (size_t)(n_seg + 1) * 4, cudaMemcpyHostToDevice, st));
+    // the host vectors must outlive the async copies
+    H3D_CHECK(cudaStreamSynchronize(st));
+
+    const int pgrid = div_up(n_prob, 128);
+    init_problems_kernel<<<pgrid, 128, 0, st>>>(prob, seg_start, n_seg, n_conds, estimator, cnt);
+    H3D_LAUNCHED("init_problems_kernel");
+    const dim3 cgrid(n_chunks, n_conds);
+    Counters h_cnt;
+
+#define DISPATCH_RC(CALL)                       \
+    if (max_rc <= 2) { CALL(2); }               \
+    else if (max_rc <= 4) { CALL(4); }          \
+    else if (max_rc <= 8) { CALL(8); }          \
+    else { CALL(16); }
+
+    if (estimator == H3D_EST_MME) {
+#define CALL(M) mme_kernel<M><<<cgrid, 256, 0, st>>>(x, f, ld, chunk_seg, chunk_lo, seg_start, cr, \
+        partial, partial_cnt, n_chunks)
+        DISPATCH_RC(CALL)
+#undef CALL
+        H3D_LAUNCHED("mme_kernel");
+        step_kernel<<<pgrid, 128, 0, st>>>(prob, seg_chunk_start, partial, partial_cnt, n_chunks, n_seg,
+                                           n_conds, estimator, 2, cnt);
+        H3D_LAUNCHED("step_kernel");
+    } else {
+        int guard = 0;
+        bool need_eq = true;
+        while (true) {
+            if (need_eq) {
+#define CALL(M) equalize_kernel<M><<<cgrid, 256, 0, st>>>(x, f, ld, chunk_seg, chunk_lo, seg_start, cr, \
+        estimator, prob, pseudo, cnt)
+                DISPATCH_RC(CALL)
+#undef CALL
+                H3D_LAUNCHED("equalize_kernel");
+                step_kernel<<<pgrid, 128, 0, st>>>(prob, seg_chunk_start, partial, partial_cnt, n_chunks,
+                                                   n_seg, n_conds, estimator, 0, cnt);
+                H3D_LAUNCHED("step_kernel");
+            }
+#define CALL(M) nll_kernel<M><<<cgrid, 256, 0, st>>>(pseudo, ld, chunk_seg, chunk_lo, seg_start, cr, prob, \
+        partial, n_chunks)
+            DISPATCH_RC(CALL)
+#undef CALL
+            H3D_LAUNCHED("nll_kernel");
+            reset_counters_kernel<<<1, 1, 0, st>>>(cnt);
+            H3D_LAUNCHED("reset_counters_kernel");
+            step_kernel<<<pgrid, 128, 0, st>>>(prob, seg_chunk_start, partial, partial_cnt, n_chunks, n_seg,
+                                               n_conds, estimator, 1, cnt);
+            H3D_LAUNCHED("step_kernel");
+            H3D_CHECK(cudaMemcpyAsync(&h_cnt, cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+            H3D_CHECK(cudaStreamSynchronize(st));
+            if (h_cnt.n_failed > 0) {
+                set_error("bounded Brent search failed for %d (distance, condition) bins "
+                          "(NaN likelihood or evaluation budget exhausted)", h_cnt.n_failed);
+                return H3D_ERR_NUMERIC;
+            }
+            if (h_cnt.n_fit_failed > 0) {
+                set_error("fit_mu_hat: %d pixels with all-zero counts inside a condition",
+                          h_cnt.n_fit_failed);
+                return H3D_ERR_NUMERIC;
+            }
+            need_eq = h_cnt.n_need_eq > 0;
+            if (!need_eq && h_cnt.n_in_brent == 0) break;
+            if (++guard > 100000) { set_error("qCML did not terminate"); return H3D_ERR_NUMERIC; }
+        }
+    }
+    collect_kernel<<<1, 256, 0, st>>>(prob, n_prob, disp_dev, stats_dev);
+    H3D_LAUNCHED("collect_kernel");
+    H3D_CHECK(cudaMemcpyAsync(disp_per_dist_host, disp_dev, (size_t)n_prob * 8, cudaMemcpyDeviceToHost, st));
+    long long h_stats[4] = {0, 0, 0, 0};
+    H3D_CHECK(cudaMemcpyAsync(h_stats, stats_dev, 3 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    H3D_CHECK(cudaStreamSynchronize(st));
+    if (stats_host) {
+        stats_host[0] = h_stats[0]; stats_host[1] = h_stats[1]; stats_host[2] = h_stats[2];
+        stats_host[3] = (long long)(h3d_launch_count() - launches_before);
+    }
+    return H3D_OK;
+}

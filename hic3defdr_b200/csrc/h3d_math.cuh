@@ -1,0 +1,404 @@
+// FP64 scalar building blocks of the scaled-NB pipeline, usable from device
+// code (the product) and from host code (tests/hostcheck only).
+//
+// Reference behaviour being reproduced (paths relative to /root/reference):
+//   fit_mu          hic3defdr/util/scaled_nb.py:139-183  (root of the score)
+//   q2q_*           hic3defdr/util/scaled_nb.py:239-275  (edgeR q2qnbinom)
+//   nb_llr          hic3defdr/util/lrt.py:46-48 + scaled_nb.py:31-33
+//   chi2_sf         hic3defdr/util/lrt.py:49 (scipy chi2.sf = gammaincc)
+//   gamma_p/gamma_q scipy.special.gammainc/gammaincc (regularised)
+//   gamma_*_inv     scipy.special.gammaincinv/gammainccinv
+// None of this is a translation of scipy/cephes: the incomplete gamma pair is
+// the textbook series + Lentz continued fraction, and the inverses are a
+// bracketed Newton iteration on the log of the tail probability.
+#pragma once
+#include <math.h>
+#include <float.h>
+
+#ifdef __CUDACC__
+#define H3D_HD __host__ __device__ __forceinline__
+#define H3D_HDN __host__ __device__ __noinline__
+#else
+#define H3D_HD inline
+#define H3D_HDN inline
+#endif
+
+namespace h3d {
+
+constexpr int kMaxReps = 16;
+constexpr double kEps = 2.220446049250313e-16;
+
+// ---------------------------------------------------------------------------
+// fit_mu: the unique positive root of
+//     g(mu) = sum_r (x_r - mu b_r) / (mu + alpha_r mu^2 b_r)
+// which is also the root of h(mu) = sum_r (x_r - mu b_r) / (1 + alpha_r b_r mu).
+// h is strictly decreasing and convex on mu > 0 (h' = -sum b(1+alpha x)/(1+a mu)^2,
+// h'' > 0), so Newton started left of the root increases monotonically to it.
+// The reference reaches the same root (to ~1e-15) with a secant sweep plus a
+// brentq fallback.  Returns the root; *status = 1 when sum(x) == 0 (the
+// reference raises there), 2 when the iteration budget ran out.
+// ---------------------------------------------------------------------------
+template <int MAXR>
+H3D_HD double fit_mu(const double* x, const double* b, const double* alpha,
+                     unsigned mask, int* status) {
+    // ``mask`` selects the replicates that take part (bit r = replicate r);
+    // arrays are indexed statically so that they stay in registers.
+    double a[MAXR], c[MAXR];
+    double sx = 0.0, sc = 0.0, mu = 0.0;
+    int nrep = 0;
+#pragma unroll
+    for (int r = 0; r < MAXR; ++r) {
+        if ((mask >> r) & 1u) {
+            a[r] = alpha[r] * b[r];
+            c[r] = b[r] * (1.0 + alpha[r] * x[r]);
+            sx += x[r];
+            sc += c[r];
+            mu += x[r] / b[r];
+            nrep += 1;
+        }
+    }
+    if (!(sx > 0.0)) { *status = 1; return 0.0; }
+    mu /= (double)nrep;                      // the reference's start, mean(x/b)
+    const double safe = sx / sc;             // Newton step from mu = 0: left of the root
+    bool left = false;                       // true once we know mu <= root
+    for (int it = 0; it < 100; ++it) {
+        double h = 0.0, dh = 0.0;
+#pragma unroll
+        for (int r = 0; r < MAXR; ++r) {
+            if ((mask >> r) & 1u) {
+                const double t = 1.0 / (1.0 + a[r] * mu);
+                h += (x[r] - mu * b[r]) * t;
+                dh -= c[r] * t * t;
+            }
+        }
+        double nxt = mu - h / dh;
+        if (!left) {
+            // first step may come from the right of the root: the tangent then
+            // lands left of the root, possibly at or below zero.
+            if (!(nxt > 0.0) || !isfinite(nxt)) nxt = safe;
+            left = true;
+            mu = nxt;
+            continue;
+        }
+        if (!(nxt > mu)) return mu;          // monotone sequence hit round-off
+        const bool done = (nxt - mu) <= 4.0 * kEps * nxt;
+        mu = nxt;
+        if (done) return mu;
+    }
+    *status = 2;
+    return mu;
+}
+
+// ---------------------------------------------------------------------------
+// Regularised incomplete gamma functions.
+// ---------------------------------------------------------------------------
+// log of x^a e^{-x} / Gamma(a).  For a >= 10 the direct form a ln x - x -
+// lgamma(a) cancels catastrophically (terms of size a ln a); there it is
+// rewritten with Stirling's series as
+//   0.5 ln(a / 2 pi) + a (ln(1+u) - u) - corr(a),   u = (x - a) / a.
+H3D_HD double log1p_minus_x(double u) {
+    if (fabs(u) < 0.25) {
+        // -u^2/2 + u^3/3 - ... via the atanh-type series in w = u / (2 + u):
+        // ln(1+u) = 2 (w + w^3/3 + w^5/5 + ...), and 2w - u = -u w
+        const double w = u / (2.0 + u);
+        const double w2 = w * w;
+        double s = 0.0;
+        for (int k = 27; k >= 3; k -= 2) s = s * w2 + 1.0 / (double)k;
+        return 2.0 * w * w2 * s - u * w;
+    }
+    return log1p(u) - u;
+}
+
+H3D_HD double gamma_log_kernel(double a, double x, double lga) {
+    if (a < 10.0) return a * log(x) - x - lga;
+    const double ia = 1.0 / a, ia2 = ia * ia;
+    const double corr = ia * (1.0 / 12.0 + ia2 * (-1.0 / 360.0 + ia2 * (1.0 / 1260.0 +
+        ia2 * (-1.0 / 1680.0 + ia2 * (1.0 / 1188.0 + ia2 * (-691.0 / 360360.0 +
+        ia2 * (1.0 / 156.0)))))));
+    const double u = (x - a) * ia;
+    return 0.5 * log(a * 0.15915494309189535) + a * log1p_minus_x(u) - corr;
+}
+
+// lower series: P(a,x) = x^a e^-x / Gamma(a+1) * sum_{n>=0} x^n / ((a+1)...(a+n))
+H3D_HD double gamma_p_series(double a, double x, double lga) {
+    const double ax = gamma_log_kernel(a, x, lga);
+    if (ax < -745.2) return 0.0;
+    double r = a, c = 1.0, ans = 1.0;
+    for (int i = 0; i < 20000; ++i) {
+        r += 1.0;
+        c *= x / r;
+        ans += c;
+        if (c <= ans * (0.5 * kEps)) break;
+    }
+    return ans * exp(ax) / a;
+}
+
+// upper continued fraction (modified Lentz):
+// Q(a,x) = x^a e^-x / Gamma(a) * 1/(x+1-a- 1(1-a)/(x+3-a- 2(2-a)/(x+5-a- ...)))
+H3D_HD double gamma_q_cf(double a, double x, double lga) {
+    const double ax = gamma_log_kernel(a, x, lga);
+    if (ax < -745.2) return 0.0;
+    const double tiny = 1e-300;
+    double bb = x + 1.0 - a;
+    double c = 1.0 / tiny;
+    double d = 1.0 / bb;
+    double h = d;
+    for (int i = 1; i < 20000; ++i) {
+        const double an = -(double)i * ((double)i - a);
+        bb += 2.0;
+        d = an * d + bb;
+        if (fabs(d) < tiny) d = tiny;
+        c = bb + an / c;
+        if (fabs(c) < tiny) c = tiny;
+        d = 1.0 / d;
+        const double del = d * c;
+        h *= del;
+        if (fabs(del - 1.0) <= kEps) break;
+    }
+    return exp(ax) * h;
+}
+
+// which evaluation is the numerically safe one for (a, x)
+H3D_HD bool gamma_use_series(double a, double x) {
+    return (x < 1.0) || (x < a);
+}
+
+H3D_HD double gamma_p(double a, double x, double lga) {
+    if (!(x > 0.0)) return (x == 0.0) ? 0.0 : NAN;
+    if (isinf(x)) return 1.0;
+    if (gamma_use_series(a, x)) return gamma_p_series(a, x, lga);
+    return 1.0 - gamma_q_cf(a, x, lga);
+}
+
+H3D_HD double gamma_q(double a, double x, double lga) {
+    if (!(x > 0.0)) return (x == 0.0) ? 1.0 : NAN;
+    if (isinf(x)) return 0.0;
+    if (gamma_use_series(a, x)) return 1.0 - gamma_p_series(a, x, lga);
+    return gamma_q_cf(a, x, lga);
+}
+
+// ---------------------------------------------------------------------------
+// Inverses.  Solve T(a, y) = t for y, where T is the lower (upper = false) or
+// upper (upper = true) regularised incomplete gamma function, by Newton on
+// log T with a maintained bracket (log T is monotone; its derivative is
+// -/+ pdf / T).  ``guess`` seeds the iteration (any positive finite value is
+// acceptable; a good one saves evaluations).
+// ---------------------------------------------------------------------------
+H3D_HD double gamma_tail(double a, double y, double lga, bool upper) {
+    return upper ? gamma_q(a, y, lga) : gamma_p(a, y, lga);
+}
+
+H3D_HD double gamma_tail_inv(double a, double t, double lga, bool upper,
+                             double guess) {
+    if (!(t > 0.0)) return (t == 0.0) ? (upper ? INFINITY : 0.0) : NAN;
+    if (t >= 1.0) return (t == 1.0) ? (upper ? 0.0 : INFINITY) : NAN;
+    const double lt = log(t);
+    double lo = 0.0, hi = INFINITY;
+    double y = (guess > 0.0 && isfinite(guess)) ? guess : a;
+    if (!upper) {
+        // far lower tail: P(a,y) ~ y^a / Gamma(a+1)
+        const double ys = exp((lt + lga + log(a)) / a);
+        if (ys < 0.2 * (a + 1.0)) y = ys;
+    }
+    if (!(y > 0.0)) y = 1.0;
+    for (int it = 0; it < 200; ++it) {
+        const double T = gamma_tail(a, y, lga, upper);
+        if (T == t) return y;
+        // bracket update: upper tail decreases in y, lower tail increases
+        const bool y_too_small = upper ? (T > t) : (T < t);
+        if (y_too_small) lo = y; else hi = y;
+        double nxt = NAN;
+        if (T > 0.0 && T < 1.0) {
+            const double lT = log(T);
+            const double lpdf = (a - 1.0) * log(y) - y - lga;
+            if (upper) {
+                // log Q is close to linear in y
+                nxt = y + (lT - lt) / exp(lpdf - lT);
+            } else {
+                // log P is close to linear in log y
+                nxt = y * exp(-(lT - lt) / (y * exp(lpdf - lT)));
+            }
+        }
+        const bool inside = (nxt > lo) && (nxt < hi);
+        if (!inside) {
+            // fall back on the bracket: bisect (geometrically when possible),
+            // or expand while one side is still open
+            if (isinf(hi)) nxt = (lo > 0.0) ? lo * 2.0 : 1.0;
+            else if (lo == 0.0) nxt = hi * 0.25;
+            else nxt = sqrt(lo) * sqrt(hi);
+        }
+        if (fabs(nxt - y) <= 2.0 * kEps * fabs(nxt)) return nxt;
+        if (!isinf(hi) && (hi - lo) <= 2.0 * kEps * hi) return nxt;
+        y = nxt;
+    }
+    return y;
+}
+
+// Wilson-Hilferty: Gamma(a,1) variate as a cube of a normal one.
+H3D_HD double wh_to_normal(double a, double x) {
+    return (cbrt(x / a) - (1.0 - 1.0 / (9.0 * a))) * 3.0 * sqrt(a);
+}
+H3D_HD double wh_from_normal(double a, double z) {
+    const double t = 1.0 - 1.0 / (9.0 * a) + z / (3.0 * sqrt(a));
+    return a * t * t * t;
+}
+
+// ---------------------------------------------------------------------------
+// q2q for one replicate of one pixel (scaled_nb.py:239-275).  mu_in/mu_out are
+// the already clamped means.  Only the tail the reference selects is
+// evaluated.  The normal-to-normal quantile map is the affine map of the
+// z-score (ndtri(ndtr(z)) == z up to round-off); where the reference's tail
+// probability underflows to zero it returns +/-inf, mimicked here.
+// ---------------------------------------------------------------------------
+H3D_HD double q2q_one(double x, double mu_in, double mu_out, double alpha) {
+    const double r_in = 1.0 + alpha * mu_in;
+    const double r_out = 1.0 + alpha * mu_out;
+    const double v_in = mu_in * r_in;
+    const double v_out = mu_out * r_out;
+    const bool right = x >= mu_in;
+    // normal part
+    const double z = (x - mu_in) / sqrt(v_in);
+    double q_norm;
+    if (fabs(z) > 38.4674056) q_norm = right ? INFINITY : -INFINITY;  // ndtr underflow
+    else q_norm = mu_out + sqrt(v_out) * z;
+    // gamma part
+    const double a_in = mu_in / r_in, a_out = mu_out / r_out;
+    const double xs = x / r_in;
+    double q_gamma;
+    if (!right && !(xs > 0.0)) {
+        q_gamma = 0.0;                       // cdf(0) = 0 -> ppf(0) = 0
+    } else {
+        const double lga_in = lgamma(a_in);
+        const double lga_out = lgamma(a_out);
+        const double t = gamma_tail(a_in, xs, lga_in, right);
+        double guess = xs * (a_out / a_in);
+        if (a_in > 2.0 && a_out > 2.0) {
+            const double g2 = wh_from_normal(a_out, wh_to_normal(a_in, xs));
+            if (g2 > 0.0 && isfinite(g2)) guess = g2;
+        }
+        q_gamma = r_out * gamma_tail_inv(a_out, t, lga_out, right, guess);
+    }
+    double out = (q_norm + q_gamma) / 2.0;
+    if (!(out >= 0.0)) out = 0.0;
+    return out;
+}
+
+// ---------------------------------------------------------------------------
+// LRT pieces.
+// ---------------------------------------------------------------------------
+// log NB pmf ratio summed over one replicate: logpmf(k; m0 f, phi) - logpmf(k; m1 f, phi)
+// with the lgamma / r ln r terms cancelled analytically (scaled_nb.py:31-33):
+//   (r + k) * log((r + m1) / (r + m0)) + k * log(m0 / m1)
+H3D_HD double nb_llr_term(double k, double m0, double m1, double phi) {
+    const double r = 1.0 / phi;
+    double t = (r + k) * log1p((m1 - m0) / (r + m0));
+    if (k > 0.0) t += k * log(m0 / m1);
+    return t;
+}
+
+// chi-square survival function, df degrees of freedom (scipy chi2.sf =
+// gammaincc(df/2, x/2); x <= 0 -> 1).
+H3D_HD double chi2_sf(double x, int df) {
+    if (isnan(x)) return NAN;
+    if (!(x > 0.0)) return 1.0;
+    if (df == 1) return erfc(sqrt(0.5 * x));
+    if (df == 2) return exp(-0.5 * x);
+    const double a = 0.5 * (double)df;
+    return gamma_q(a, 0.5 * x, lgamma(a));
+}
+
+// ---------------------------------------------------------------------------
+// One evaluation step of scipy's bounded Brent minimiser
+// (scipy/optimize/_optimize.py:2289-2436, method='bounded', xatol=1e-5,
+// maxiter=500), restructured as a resumable state machine: ``begin`` yields
+// the first abscissa, ``advance`` consumes f(x_eval) and either yields the next
+// abscissa (returns true) or finishes (returns false; xf is the minimiser).
+// ---------------------------------------------------------------------------
+struct BrentState {
+    double a, b, xf, fx, nfc, fnfc, fulc, ffulc, e, rat, x_eval;
+    int num;      // function evaluations so far
+    int flag;     // 0 ok, 1 maxfun reached, 2 NaN
+};
+
+H3D_HD bool brent_propose(BrentState& s, double xatol) {
+    // loop head of the reference: test convergence, otherwise choose x_eval
+    const double sqrt_eps = sqrt(2.2e-16);
+    const double golden_mean = 0.5 * (3.0 - sqrt(5.0));
+    const double xm = 0.5 * (s.a + s.b);
+    const double tol1 = sqrt_eps * fabs(s.xf) + xatol / 3.0;
+    const double tol2 = 2.0 * tol1;
+    if (!(fabs(s.xf - xm) > (tol2 - 0.5 * (s.b - s.a)))) return false;
+    bool golden = true;
+    if (fabs(s.e) > tol1) {
+        golden = false;
+        double r = (s.xf - s.nfc) * (s.fx - s.ffulc);
+        double q = (s.xf - s.fulc) * (s.fx - s.fnfc);
+        double p = (s.xf - s.fulc) * q - (s.xf - s.nfc) * r;
+        q = 2.0 * (q - r);
+        if (q > 0.0) p = -p;
+        q = fabs(q);
+        r = s.e;
+        s.e = s.rat;
+        if ((fabs(p) < fabs(0.5 * q * r)) && (p > q * (s.a - s.xf)) &&
+            (p < q * (s.b - s.xf))) {
+            s.rat = (p + 0.0) / q;
+            const double x = s.xf + s.rat;
+            if (((x - s.a) < tol2) || ((s.b - x) < tol2)) {
+                const double dm = xm - s.xf;
+                const double si = (dm > 0.0) - (dm < 0.0) + (dm == 0.0);
+                s.rat = tol1 * si;
+            }
+        } else {
+            golden = true;
+        }
+    }
+    if (golden) {
+        s.e = (s.xf >= xm) ? (s.a - s.xf) : (s.b - s.xf);
+        s.rat = golden_mean * s.e;
+    }
+    const double si = (s.rat > 0.0) - (s.rat < 0.0) + (s.rat == 0.0);
+    s.x_eval = s.xf + si * fmax(fabs(s.rat), tol1);
+    return true;
+}
+
+H3D_HD void brent_begin(BrentState& s, double lo, double hi) {
+    const double golden_mean = 0.5 * (3.0 - sqrt(5.0));
+    s.a = lo; s.b = hi;
+    s.fulc = lo + golden_mean * (hi - lo);
+    s.nfc = s.fulc; s.xf = s.fulc;
+    s.rat = 0.0; s.e = 0.0;
+    s.x_eval = s.xf;
+    s.num = 0; s.flag = 0;
+    s.fx = s.fnfc = s.ffulc = 0.0;
+}
+
+// returns true when another evaluation at s.x_eval is wanted
+H3D_HD bool brent_advance(BrentState& s, double fu, double xatol, int maxfun) {
+    if (s.num == 0) {
+        s.fx = fu; s.num = 1;
+        s.ffulc = s.fnfc = fu;
+        if (isnan(fu)) { s.flag = 2; return false; }
+        return brent_propose(s, xatol);
+    }
+    const double x = s.x_eval;
+    s.num += 1;
+    if (fu <= s.fx) {
+        if (x >= s.xf) s.a = s.xf; else s.b = s.xf;
+        s.fulc = s.nfc; s.ffulc = s.fnfc;
+        s.nfc = s.xf; s.fnfc = s.fx;
+        s.xf = x; s.fx = fu;
+    } else {
+        if (x < s.xf) s.a = x; else s.b = x;
+        if ((fu <= s.fnfc) || (s.nfc == s.xf)) {
+            s.fulc = s.nfc; s.ffulc = s.fnfc;
+            s.nfc = x; s.fnfc = fu;
+        } else if ((fu <= s.ffulc) || (s.fulc == s.xf) || (s.fulc == s.nfc)) {
+            s.fulc = x; s.ffulc = fu;
+        }
+    }
+    if (isnan(fu) || isnan(s.fx) || isnan(s.xf)) { s.flag = 2; return false; }
+    if (s.num >= maxfun) { s.flag = 1; return false; }
+    return brent_propose(s, xatol);
+}
+
+}  // namespace h3d

@@ -1,0 +1,222 @@
+/*
+ * libh3d -- C ABI of the B200-native implementation of the per-pixel
+ * statistical pipeline behind HiC3DeFDR.run_to_qvalues()
+ * (thomasgilgenast/hic3defdr v0.2.1).
+ *
+ * The reference is pure Python and has no FFI layer; the drop-in boundary is
+ * its Python class (hic3defdr/analysis/constructor.py:12-86) and its .npy
+ * files.  Each entry point below replaces the arithmetic of the reference
+ * function cited next to it; hic3defdr_b200/analysis.py (the host-side mirror
+ * of the reference class) is the only caller.  INTEGRATION.md shows the
+ * ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every array pointer is a DEVICE pointer
+ *     unless its name ends in _host; the caller owns every buffer;
+ *   - every call enqueues its kernels on ``stream`` (a cudaStream_t) and
+ *     returns without synchronising unless stated otherwise;
+ *   - return value 0 on success, negative H3D_ERR_* otherwise;
+ *     h3d_last_error() returns a thread-local message;
+ *   - scratch memory: ``ws``/``ws_bytes`` is a caller-owned device buffer of at
+ *     least h3d_*_ws_bytes(...) bytes;
+ *   - matrices are C-order (row-major), pixels x replicates unless stated.
+ */
+#ifndef H3D_H
+#define H3D_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* h3d_stream_t; /* cudaStream_t */
+
+#define H3D_OK 0
+#define H3D_ERR_ARG (-1)
+#define H3D_ERR_CUDA (-2)
+#define H3D_ERR_WORKSPACE (-3)
+#define H3D_ERR_NUMERIC (-4)
+
+#define H3D_MAX_REPS 16
+#define H3D_MAX_CONDS 8
+
+/* element types of CSR ``data`` arrays */
+#define H3D_DTYPE_I64 0
+#define H3D_DTYPE_F64 1
+#define H3D_DTYPE_I32 2
+#define H3D_DTYPE_F32 3
+
+/* size-factor modes: hic3defdr/util/scaling.py:27-149 */
+#define H3D_NORM_CONDITIONAL_MOR 0
+#define H3D_NORM_CONDITIONAL_SCALING 1
+#define H3D_NORM_MEDIAN_OF_RATIOS 2
+#define H3D_NORM_SIMPLE_SCALING 3
+
+/* ---- library ---------------------------------------------------------- */
+int h3d_version(void);
+const char* h3d_last_error(void);
+/* number of kernels this library has launched since load / last reset */
+unsigned long long h3d_launch_count(void);
+void h3d_reset_launch_count(void);
+
+/* ---- prepare_data ------------------------------------------------------ */
+
+/* CoreHiC3DeFDR.load_bias filter, hic3defdr/analysis/core.py:58-59.
+ * bias: (n_bins, n_reps), filtered in place. */
+int h3d_bias_filter(double* bias, int n_bins, int n_reps, double bias_thresh,
+                    h3d_stream_t stream);
+
+/* sparse_union + deconvolute + wipe_distances, hic3defdr/util/matrices.py:92-129,
+ * 8-38, 41-62 (mean_thresh = 0), pass 1: number of union pixels per row and
+ * their exclusive prefix.  indptr_host/indices_host/data_host are HOST arrays
+ * of n_reps DEVICE pointers (one CSR matrix per replicate, canonical format).
+ * row_offset: (n_bins + 1) int32; row_offset[n_bins] = number of union pixels. */
+int h3d_union_count(int n_reps, const void* const* indptr_host, int indptr_is64,
+                    const int* const* indices_host, const void* const* data_host,
+                    int data_dtype, const double* bias, int n_bins, int dist_max,
+                    int* row_offset, void* ws, size_t ws_bytes, h3d_stream_t stream);
+size_t h3d_union_ws_bytes(int n_bins);
+
+/* pass 2: emits row, col (int32, (row, col) order), dist = col - row (may be
+ * NULL), raw (int64, truncating; hic3defdr/analysis/analysis.py:92-95) and
+ * balanced (float64; :98-101). */
+int h3d_union_emit(int n_reps, const void* const* indptr_host, int indptr_is64,
+                   const int* const* indices_host, const void* const* data_host,
+                   int data_dtype, const double* bias, int n_bins, int dist_max,
+                   const int* row_offset, int* row, int* col, int* dist,
+                   long long* raw, double* balanced, h3d_stream_t stream);
+
+/* Size factors, hic3defdr/util/scaling.py:27-149 with equal_bin
+ * (util/binning.py:4-25, canonical stable tie-break).  dist: (n_px) int32,
+ * balanced: (n_px, n_reps).  Output sf_table:
+ *   conditional modes: (dist_max + 1, n_reps), the size factor of every
+ *                      distance (n_bins > 0: interpolated between bins;
+ *                      n_bins == 0: exact-distance groups, NaN where empty);
+ *   other modes:       (n_reps).
+ * Synchronises the stream once (group bookkeeping is read back). */
+int h3d_size_factors(const int* dist, const double* balanced, long long n_px,
+                     int n_reps, int dist_max, int n_bins, int norm,
+                     double* sf_table, void* ws, size_t ws_bytes,
+                     h3d_stream_t stream);
+size_t h3d_size_factors_ws_bytes(long long n_px, int n_reps, int dist_max);
+
+/* scaled = balanced / size_factors, per-condition means and disp_idx,
+ * hic3defdr/analysis/analysis.py:109-115.  ``data`` holds balanced on entry
+ * and scaled on exit.  size_factors_out ((n_px, n_reps)) may be NULL.
+ * design: (n_reps, n_conds) bytes. */
+int h3d_scale_filter(const int* row, const int* col, double* data,
+                     const double* sf_table, int sf_per_dist,
+                     const unsigned char* design_host, long long n_px, int n_reps,
+                     int n_conds, int dist_max, double mean_thresh, int dist_min,
+                     double* size_factors_out, unsigned char* disp_idx,
+                     h3d_stream_t stream);
+
+/* indices of the set entries of a boolean mask, in order (the device form of
+ * ``array[disp_idx]``).  n_set_out: one int64 on the device. */
+int h3d_mask_to_index(const unsigned char* mask, long long n, int* index_out,
+                      long long* n_set_out, void* ws, size_t ws_bytes,
+                      h3d_stream_t stream);
+size_t h3d_mask_to_index_ws_bytes(long long n);
+
+/* loop_idx, hic3defdr/analysis/analysis.py:117-125: membership of
+ * (row, col)[index] in a sorted set of row * 2^32 + col keys. */
+int h3d_loop_membership(const int* row, const int* col, const int* index,
+                        long long n, const long long* sorted_keys, long long n_keys,
+                        unsigned char* out, h3d_stream_t stream);
+
+/* ---- estimate_disp ------------------------------------------------------ */
+
+/* Combined factor f = bias[row] * bias[col] * size_factors
+ * (hic3defdr/analysis/analysis.py:181-183, 272-275) and the raw counts of the
+ * selected pixels, written replicate-major (SoA: x_out[r * ld + pos]) at
+ * positions dest[i] (or i when dest is NULL); dist_out[pos] = col - row.
+ * x_out = f_out = NULL computes the distances only. */
+int h3d_gather_counts_factors(const int* row, const int* col, const int* index,
+                              long long n_sel, const long long* raw,
+                              const double* size_factors, int sf_per_pixel,
+                              const double* bias, int n_reps, const int* dest,
+                              long long ld, double* x_out, double* f_out,
+                              int* dist_out, h3d_stream_t stream);
+
+/* Stable rank of every element when sorting by an integer key in
+ * [0, n_keys): rank_out[i] = position of element i; key_start: (n_keys + 1)
+ * int64 group boundaries.  Used for equal_bin (util/binning.py:25) and for
+ * pooling pixels by distance (analysis/analysis.py:196-197). */
+int h3d_stable_rank(const int* keys, long long n, int n_keys, int* rank_out,
+                    long long* key_start, void* ws, size_t ws_bytes,
+                    h3d_stream_t stream);
+size_t h3d_stable_rank_ws_bytes(long long n, int n_keys);
+
+/* qCML / CML / MME dispersion per (distance, condition) segment,
+ * hic3defdr/util/dispersion.py:10-131 with equalize/q2qnbinom
+ * (util/scaled_nb.py:186-275).  x, f: SoA (n_reps, ld) pooled by distance
+ * (segment d = [seg_start_host[d], seg_start_host[d + 1])).
+ * disp_per_dist_host: (n_seg, n_conds) HOST output, NaN for empty segments.
+ * stats_host (may be NULL): 4 int64 = {outer iterations, NLL evaluations,
+ * pixel-equalisations, kernel launches}.  Synchronises. */
+#define H3D_EST_QCML 0
+#define H3D_EST_CML 1
+#define H3D_EST_MME 2
+int h3d_estimate_dispersion(const double* x, const double* f, long long ld,
+                            const long long* seg_start_host, int n_seg,
+                            const unsigned char* design_host, int n_reps,
+                            int n_conds, int estimator,
+                            double* disp_per_dist_host, long long* stats_host,
+                            void* ws, size_t ws_bytes, h3d_stream_t stream);
+size_t h3d_estimate_dispersion_ws_bytes(long long n_px, int n_seg, int n_reps,
+                                        int n_conds);
+
+/* lowess (lib5c.util.lowess.lowess as called at hic3defdr/util/lowess.py:72):
+ * x sorted ascending, n points, returns fitted values y_fit (device). */
+int h3d_lowess(const double* x, const double* y, int n, double frac, int it,
+               double delta, double* y_fit, void* ws, size_t ws_bytes,
+               h3d_stream_t stream);
+size_t h3d_lowess_ws_bytes(int n);
+
+/* disp[:, c] = disp_fn_c(dist) for integer distances: gather from a
+ * (dist_max + 1, n_conds) table (hic3defdr/analysis/analysis.py:218). */
+int h3d_gather_table(const int* dist, long long n, const double* table,
+                     int n_cols, int n_rows, double* out, h3d_stream_t stream);
+
+/* ---- lrt ---------------------------------------------------------------- */
+
+/* fit_mu_hat, hic3defdr/util/scaled_nb.py:71-183.  x, b: (n, n_reps);
+ * alpha: (n, n_reps) when alpha_stride_px = n_reps, broadcast forms with
+ * alpha_stride_px / alpha_stride_rep in {0, 1, n_reps}.  status: number of
+ * pixels without a positive root (one int32 on the device, accumulated). */
+int h3d_fit_mu_hat(const double* x, const double* b, const double* alpha,
+                   long long alpha_stride_px, long long alpha_stride_rep,
+                   long long n, int n_reps, double* mu_out, int* n_failed,
+                   h3d_stream_t stream);
+
+/* lrt, hic3defdr/util/lrt.py:7-50: raw (n, n_reps) float64 counts, f
+ * (n, n_reps), disp (n, n_conds) per-condition dispersions (the reference's
+ * ``disp @ design.T`` widening happens inside). */
+int h3d_lrt(const double* raw, const double* f, const double* disp,
+            const unsigned char* design_host, long long n, int n_reps, int n_conds,
+            int refit_mu, double* pvalues, double* llr, double* mu_hat_null,
+            double* mu_hat_alt, int* n_failed, h3d_stream_t stream);
+
+/* The same test fused with its input gathers for the pipeline
+ * (hic3defdr/analysis/analysis.py:261-278): reads the union-aligned arrays
+ * through ``index`` (the disp_idx positions). */
+int h3d_lrt_fused(const int* row, const int* col, const int* index, long long n_sel,
+                  const long long* raw, const double* size_factors, int sf_per_pixel,
+                  const double* bias, const double* disp,
+                  const unsigned char* design_host, int n_reps, int n_conds,
+                  int refit_mu, double* pvalues, double* llr, double* mu_hat_null,
+                  double* mu_hat_alt, int* n_failed, h3d_stream_t stream);
+
+/* ---- bh ----------------------------------------------------------------- */
+
+/* Benjamini-Hochberg q-values over the finite entries of p
+ * (lib5c adjust_pvalues, call site hic3defdr/analysis/analysis.py:300). */
+int h3d_bh(const double* p, long long n, double* q, void* ws, size_t ws_bytes,
+           h3d_stream_t stream);
+size_t h3d_bh_ws_bytes(long long n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* H3D_H */

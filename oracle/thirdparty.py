@@ -29,7 +29,7 @@ def adjust_pvalues(pvalues):
     (method='fdr_bh') applied to the finite entries; non-finite entries stay
     NaN.  Call site: hic3defdr/analysis/analysis.py:300.  PARITY UNPINNED.
 
-    Benjamini-Hochberg: sort ascending, q_(i) = p_(i) * n / i, enforce
+    Benjamini-Hochberg: sort ascending, q_(i) = p_(i) / (i / n), enforce
     monotonicity with a running minimum from the largest p downwards, clip at
     1, undo the sort.
     """
@@ -41,7 +41,7 @@ def adjust_pvalues(pvalues):
     if n == 0:
         return q
     order = np.argsort(pf, kind='stable')
-    ranked = pf[order] * (float(n) / np.arange(1, n + 1))
+    ranked = pf[order] / (np.arange(1, n + 1) / float(n))   # p / ecdf
     ranked = np.minimum.accumulate(ranked[::-1])[::-1]
     ranked[ranked > 1] = 1
     out = np.empty(n)

@@ -1,0 +1,43 @@
+// TEST TOOL: compiles the scalar FP64 building blocks of
+// hic3defdr_b200/csrc/h3d_math.cuh as HOST code so that their algorithms can be
+// checked against scipy on a machine without a GPU.  Never used by the product.
+#include "../../hic3defdr_b200/csrc/h3d_math.cuh"
+extern "C" {
+void hc_fit_mu(const double* x, const double* b, const double* alpha, int n, int R,
+               double* out, int* status) {
+    for (int i = 0; i < n; ++i) {
+        int st = 0;
+        out[i] = h3d::fit_mu<h3d::kMaxReps>(x + (long)i * R, b + (long)i * R,
+                                            alpha + (long)i * R, (1u << R) - 1u, &st);
+        status[i] = st;
+    }
+}
+void hc_gamma_pq(const double* a, const double* x, int n, double* p, double* q) {
+    for (int i = 0; i < n; ++i) {
+        double lga = lgamma(a[i]);
+        p[i] = h3d::gamma_p(a[i], x[i], lga);
+        q[i] = h3d::gamma_q(a[i], x[i], lga);
+    }
+}
+void hc_gamma_inv(const double* a, const double* t, int n, int upper, double* y) {
+    for (int i = 0; i < n; ++i)
+        y[i] = h3d::gamma_tail_inv(a[i], t[i], lgamma(a[i]), upper != 0, a[i]);
+}
+void hc_q2q(const double* x, const double* mu_in, const double* mu_out, double alpha,
+            int n, double* out) {
+    for (int i = 0; i < n; ++i) out[i] = h3d::q2q_one(x[i], mu_in[i], mu_out[i], alpha);
+}
+void hc_chi2_sf(const double* x, int n, int df, double* out) {
+    for (int i = 0; i < n; ++i) out[i] = h3d::chi2_sf(x[i], df);
+}
+// drives the Brent state machine with a callback
+typedef double (*hc_fn)(double);
+double hc_brent(hc_fn f, double lo, double hi, double xatol, int maxfun, int* nfev, int* flag) {
+    h3d::BrentState s;
+    h3d::brent_begin(s, lo, hi);
+    bool more = true;
+    while (more) more = h3d::brent_advance(s, f(s.x_eval), xatol, maxfun);
+    *nfev = s.num; *flag = s.flag;
+    return s.xf;
+}
+}

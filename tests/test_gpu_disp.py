@@ -1,0 +1,150 @@
+"""GPU parity: dispersion estimation (qCML / CML / MME), the lowess trend and
+BH through the C ABI against recorded reference outputs and the oracle."""
+import numpy as np
+import pytest
+
+from oracle import pipeline as op
+from oracle.thirdparty import lowess as oracle_lowess
+from tests.helpers import load_pipeline_golden, load_stage_golden
+
+pytestmark = pytest.mark.gpu
+
+# dispersion tolerance: the reference's own qCML result moves by 6e-10..8e-9
+# relative when the pixel order is permuted, and
+# Brent stops at xatol = 1e-5; 1e-7 relative is the stage-isolated bar.
+DISP_RTOL = 1e-7
+
+
+def test_qcml_single_bins_vs_recorded_reference():
+    from hic3defdr_b200 import ops
+    s = load_stage_golden()
+    assert ops.qcml(s['bin_x'], s['bin_f']) == \
+        pytest.approx(float(s['qcml']), rel=DISP_RTOL)
+    assert ops.qcml(s['bin4_x'], s['bin4_f']) == \
+        pytest.approx(float(s['qcml4']), rel=DISP_RTOL)
+
+
+def test_cml_on_recorded_pseudodata():
+    from hic3defdr_b200 import ops
+    s = load_stage_golden()
+    assert ops.cml(s['equalize_0.01']) == \
+        pytest.approx(float(s['cml_pseudo']), rel=DISP_RTOL)
+
+
+def test_mme_vs_oracle():
+    from hic3defdr_b200 import ops
+    s = load_stage_golden()
+    assert ops.mme(s['bin4_x'], s['bin4_f']) == \
+        pytest.approx(op.mme(s['bin4_x'], s['bin4_f']), rel=1e-12)
+
+
+def test_pooled_estimate_vs_recorded_reference():
+    """all (distance, condition) bins of the golden data set in lock step"""
+    import torch
+    from hic3defdr_b200 import ops
+    gold = load_pipeline_golden()
+    g = gold['g']
+    raws, fs, dists = [], [], []
+    for c, (mats, bias_raw) in zip(gold['chroms'], gold['inputs']):
+        di = g['disp_idx_%s' % c]
+        bias = op.filter_bias(bias_raw, 0.1)
+        r, cc = g['row_%s' % c][di], g['col_%s' % c][di]
+        raws.append(g['raw_%s' % c][di])
+        fs.append(op.combined_factor(bias, r, cc, g['size_factors_%s' % c][di]))
+        dists.append(cc - r)
+    raw, f, dist = np.concatenate(raws), np.concatenate(fs), \
+        np.concatenate(dists)
+    dmax = gold['dist_max']
+    rank, start = ops.stable_rank(dist.astype(np.int32), dmax + 1)
+    rk = rank.cpu().numpy()
+    x_soa = np.empty((raw.shape[1], len(dist)))
+    f_soa = np.empty_like(x_soa)
+    x_soa[:, rk] = raw.T
+    f_soa[:, rk] = f.T
+    got, stats = ops.estimate_dispersion(ops.dev(x_soa), ops.dev(f_soa),
+                                         start.cpu().numpy(), gold['design'])
+    want = g['disp_per_dist']
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    ok = np.isfinite(want)
+    np.testing.assert_allclose(got[ok], want[ok], rtol=DISP_RTOL)
+    assert stats['outer_iterations'] >= ok.sum()
+    # the other estimators against the oracle on the same pooled data
+    for est, fn in (('mme', op.mme),):
+        got, _ = ops.estimate_dispersion(ops.dev(x_soa), ops.dev(f_soa),
+                                         start.cpu().numpy(), gold['design'],
+                                         est)
+        for d in (4, 10, dmax):
+            for c in range(2):
+                reps = gold['design'][:, c]
+                sel = dist == d
+                assert got[d, c] == pytest.approx(
+                    fn(raw[sel][:, reps], f[sel][:, reps]), rel=1e-11)
+
+
+def test_lowess_vs_oracle():
+    from hic3defdr_b200.trend import _device_lowess
+    rng = np.random.default_rng(8)
+    for n, frac, dfrac in ((50, 0.3, 0.01), (400, 0.1, 0.01), (1500, 0.6, 0.0),
+                           (300, 0.05, 0.02)):
+        x = np.sort(rng.integers(0, 200, size=n)).astype(float)
+        y = 0.02 + 1e-4 * x + rng.normal(0, 1e-3, n)
+        y[rng.integers(0, n, 5)] += 0.02          # outliers
+        delta = (x.max() - x.min()) * dfrac
+        want = oracle_lowess(y, x, frac=frac, it=3, delta=delta)
+        sx, sy = _device_lowess(x, y, frac, dfrac)
+        np.testing.assert_array_equal(sx, want[:, 0])
+        np.testing.assert_allclose(sy, want[:, 1], rtol=1e-9)
+
+
+def test_trend_fit_vs_recorded_reference():
+    from hic3defdr_b200.trend import lowess_fit, weighted_lowess_fit
+    s = load_stage_golden()
+    xs, ys, xq = s['trend_x'], s['trend_y'], s['trend_q']
+    fn = weighted_lowess_fit(xs, ys, left_boundary=ys[0], auto_frac_factor=15.)
+    np.testing.assert_allclose(fn(xq), s['trend_weighted'], rtol=1e-9)
+    fn = weighted_lowess_fit(xs, ys, left_boundary=ys[0], frac=0.2)
+    np.testing.assert_allclose(fn(xq), s['trend_weighted_frac0.2'], rtol=1e-9)
+    fn = lowess_fit(xs, ys, left_boundary=ys[0])
+    np.testing.assert_allclose(fn(xq), s['trend_plain'], rtol=1e-9)
+    import dill
+    fn2 = dill.loads(dill.dumps(fn))
+    np.testing.assert_array_equal(fn2(xq), fn(xq))
+
+
+@pytest.mark.parametrize('n', [1, 2, 1000, 300001])
+def test_bh_vs_oracle(n):
+    from hic3defdr_b200 import ops
+    rng = np.random.default_rng(n)
+    p = rng.random(n) ** 4
+    if n > 10:
+        p[::13] = np.nan
+        p[5] = p[6] = p[7]          # ties
+        p[9] = 0.0
+        p[10] = 1.0
+        p[11] = np.inf
+    q = ops.adjust_pvalues(p).cpu().numpy()
+    want = op.bh(p)
+    assert np.array_equal(np.isnan(q), np.isnan(want))
+    ok = np.isfinite(want)
+    # tolerance 1e-9 (north_star); same IEEE operations -> expected exact
+    np.testing.assert_allclose(q[ok], want[ok], rtol=1e-12)
+
+
+def test_bh_properties_large():
+    """size-independent properties at a size the oracle is slow for"""
+    from hic3defdr_b200 import ops
+    import torch
+    n = 20_000_000
+    g = torch.Generator(device='cuda').manual_seed(1)
+    p = torch.rand(n, generator=g, device='cuda', dtype=torch.float64) ** 3
+    q = ops.adjust_pvalues(p)
+    assert bool((q >= p).all()) and bool((q <= 1).all())
+    order = torch.argsort(p)
+    assert bool((torch.diff(q[order]) >= 0).all())
+    # q of the largest p equals that p (n / n)
+    i = int(order[-1])
+    assert float(q[i]) == pytest.approx(float(p[i]), rel=1e-15)
+    # ranks recovered from q for a strictly separated subset
+    k = 1000
+    j = int(order[k])
+    assert float(q[j]) <= float(p[j]) * n / (k + 1) * (1 + 1e-12)
