@@ -1,0 +1,403 @@
+"""
+bench.py -- pixels/sec through run_to_qvalues (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                    [--workload mouse10kb|chr18_19|tiny]
+
+A step = one pass of prepare_data -> estimate_disp -> lrt -> bh over the whole
+synthetic workload (default: BASELINE.json configs[1], mouse genome-wide
+chr1-19,X at 10 kb, 2-vs-2 replicates, default filtering).
+
+  value     union pixels / s, inputs (per-replicate CSR + bias) already resident
+            in HBM, all outputs left resident in HBM; CUDA-event timed, max over
+            ranks
+  e2e       the same pass through the host-buffer entry (pinned host CSR/bias
+            in, every output array copied back to pinned host memory), copies
+            inside the timed region
+  roofline  the dominant kernel (equalize_kernel, FP64-pipe bound): model FP64
+            flops / its CUDA-event time, against the FP64 FMA rate measured in
+            this run (MEASURED_PEAKS.json has no FP64 entry)
+  cpu_baseline  the oracle port timed on one host core on a bounded sample of
+            the same workload
+--impl reference: the oracle port with all host threads (the reference is pure
+Python and cannot be installed on the GPU box; oracle/ is its restatement,
+pinned bitwise to it by tests/golden).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+from hic3defdr_b200.synth import MM10_10KB  # noqa: E402
+
+# SURVEY.md section 8(d), cost model v1: FP64 instruction-equivalents of one
+# pixel-equalisation (fit_mu_hat 500 + gmean 85 + 2 x q2q 2150) for R_c = 2;
+# FMA = 2 flops.
+EQUALIZE_INST_EQ_PER_PX = 4885.0
+
+WORKLOADS = {
+    'mouse10kb': dict(chroms=MM10_10KB, n_reps=4, dist_max=200, amp=300.0,
+                      desc='synthetic mouse genome-wide (chr1-19,X) 10 kb, '
+                           '2-vs-2 reps, default filtering'),
+    'chr18_19': dict(chroms={k: MM10_10KB[k] for k in ('chr18', 'chr19')},
+                     n_reps=4, dist_max=200, amp=300.0,
+                     desc='synthetic 2-vs-2 reps, chr18+chr19 mouse-sized, '
+                          '10 kb, dist cap 200 bins'),
+    'tiny': dict(chroms={'chrA': 1500, 'chrB': 1100}, n_reps=4, dist_max=60,
+                 amp=200.0, desc='tiny smoke workload'),
+}
+CPU_SAMPLE = dict(chroms={'s1': 700, 's2': 500}, dist_max=200)
+
+
+# --------------------------------------------------------------------------
+# synthetic inputs, generated on the device (same sampling model as
+# hic3defdr_b200/synth.py; plumbing, outside every timed region)
+# --------------------------------------------------------------------------
+def gen_chrom_device(n, n_reps, dist_max, seed, amp, pad=5):
+    import torch
+    g = torch.Generator(device='cuda').manual_seed(seed)
+    width = dist_max + pad + 1
+    d = torch.arange(width, device='cuda', dtype=torch.float64)
+    row = torch.arange(n, device='cuda')
+    col = row[:, None] + torch.arange(width, device='cuda')[None, :]
+    valid = col < n
+    mu = (amp / (1.0 + d))[None, :]
+    phi = (0.01 + 1e-4 * d)[None, :]
+    bias = torch.exp(0.2 * torch.randn((n, n_reps), generator=g, device='cuda',
+                                       dtype=torch.float64))
+    bad = torch.rand((n, n_reps), generator=g, device='cuda') < 0.01
+    bias[bad] = 0.05
+    mats = []
+    colc = col.clamp(max=n - 1)
+    for r in range(n_reps):
+        depth = 0.8 + 0.1 * r if n_reps <= 4 else 0.7 + 0.08 * r
+        m = mu * bias[:, r][:, None] * bias[:, r][colc] * depth
+        shape = (1.0 / phi).expand_as(m).contiguous()
+        lam = torch._standard_gamma(shape, generator=g) * (m * phi)
+        x = torch.poisson(lam, generator=g)
+        keep = valid & (x > 0)
+        counts = keep.sum(dim=1)
+        indptr = torch.zeros(n + 1, dtype=torch.int64, device='cuda')
+        indptr[1:] = torch.cumsum(counts, 0)
+        mats.append(dict(indptr=indptr.to(torch.int32),
+                         indices=col[keep].to(torch.int32),
+                         data=x[keep].to(torch.int64)))
+    return mats, bias
+
+
+class HostChrom(object):
+    """pinned host copy of one chromosome's inputs (for the e2e leg)"""
+
+    def __init__(self, mats, bias):
+        pin = lambda t: t.cpu().pin_memory()
+        self.mats = [{k: pin(v) for k, v in m.items()} for m in mats]
+        self.bias = pin(bias)
+        self.nbytes = sum(v.numel() * v.element_size()
+                          for m in self.mats for v in m.values()) + \
+            self.bias.numel() * 8
+
+
+def device_csr(mats, n):
+    """ops.DeviceCSR from device (or pinned host) tensors without scipy."""
+    from hic3defdr_b200 import ops
+    c = ops.DeviceCSR.__new__(ops.DeviceCSR)
+    c.n_reps = len(mats)
+    c.n_bins = n
+    c.indptr = [m['indptr'].cuda(non_blocking=True) for m in mats]
+    c.indices = [m['indices'].cuda(non_blocking=True) for m in mats]
+    c.data = [m['data'].cuda(non_blocking=True) for m in mats]
+    c.dtype = np.dtype(np.int64)
+    c.is64 = 0
+    c.nnz = sum(int(d.numel()) for d in c.data)
+    return c
+
+
+OUTPUT_NAMES = ('row', 'col', 'raw', 'size_factors', 'scaled', 'disp_idx',
+                'disp', 'pvalues', 'llr', 'mu_hat_null', 'mu_hat_alt',
+                'qvalues')
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index=0):
+        super(ClockSampler, self).__init__(daemon=True)
+        self.samples, self.reasons, self.stop_flag = [], set(), False
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(
+                self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: 'hw_slowdown',
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: 'hw_thermal_slowdown',
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: 'sw_thermal_slowdown',
+            nv.nvmlClocksThrottleReasonSwPowerCap: 'sw_power_cap',
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(
+                    self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        return dict(sm_mhz=float(np.median(self.samples))
+                    if self.samples else None,
+                    sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons))
+
+
+# --------------------------------------------------------------------------
+# reference arm / cpu baseline (oracle port on host cores)
+# --------------------------------------------------------------------------
+def cpu_inputs():
+    from hic3defdr_b200.synth import make_chrom
+    ins = []
+    for i, (c, n) in enumerate(CPU_SAMPLE['chroms'].items()):
+        mats, bias, _ = make_chrom(n, 4, CPU_SAMPLE['dist_max'],
+                                   seed=20261018 + 2000 + 100 * i, amp=300.0)
+        ins.append((mats, bias))
+    return ins
+
+
+def time_oracle(n_threads):
+    from oracle import parallel
+    design = np.array([[1, 0], [1, 0], [0, 1], [0, 1]], dtype=bool)
+    ins = cpu_inputs()
+    t0 = time.perf_counter()
+    res = parallel.run_to_qvalues(ins, design, dist_max=CPU_SAMPLE['dist_max'],
+                                  n_threads=n_threads)
+    dt = time.perf_counter() - t0
+    n_px = sum(len(st['row']) for st in res['chroms'])
+    return n_px, dt
+
+
+def sample_desc():
+    return ('%d-bin + %d-bin chromosomes of the same generator, 2-vs-2, '
+            'dist cap %d bins, full run_to_qvalues arithmetic in memory'
+            % (CPU_SAMPLE['chroms']['s1'], CPU_SAMPLE['chroms']['s2'],
+               CPU_SAMPLE['dist_max']))
+
+
+def run_reference(args, cfg):
+    if int(os.environ.get('RANK', '0')) != 0:
+        return
+    cores = os.cpu_count() or 1
+    rates, times = [], []
+    for _ in range(args.warmup):
+        pass        # nothing to warm: every step is a fresh process pool
+    for _ in range(args.steps):
+        n_px, dt = time_oracle(-1)
+        rates.append(n_px / dt)
+        times.append(dt)
+    value = float(np.mean(rates))
+    line = dict(
+        impl='reference', metric='pixels/sec through run_to_qvalues',
+        value=value, unit='pixels/s', n_gpus=args.gpus, steps=args.steps,
+        warmup=args.warmup, ms_per_step=1e3 * float(np.mean(times)),
+        higher_is_better=True, scaling='strong', vs_baseline=None,
+        dtype='f64', data='synthetic',
+        config=dict(workload=cfg['desc'], timing='host wall clock'),
+        cpu_baseline=dict(value=value, unit='pixels/s', cores=cores,
+                          kind='port', sample=sample_desc()),
+        e2e=dict(value=value, unit='pixels/s', h2d_bytes_per_step=0,
+                 d2h_bytes_per_step=0),
+        gpu_launches=0)
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200')
+    ap.add_argument('--workload', default='mouse10kb')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    cfg = WORKLOADS[args.workload]
+    if args.impl == 'reference':
+        run_reference(args, cfg)
+        return
+
+    import torch
+    import torch.distributed as td
+    from hic3defdr_b200 import dist as hdist
+    from hic3defdr_b200 import engine, ops
+    from hic3defdr_b200._native import lib
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        td.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    rank = hdist.rank()
+    design = np.array([[1, 0], [1, 0], [0, 1], [0, 1]], dtype=bool)
+    kw = dict(dist_max=cfg['dist_max'])
+
+    # ---- inputs: this rank's chromosomes, resident in HBM ---------------
+    names = list(cfg['chroms'].keys())
+    owner = hdist.lpt_assign([cfg['chroms'][c] for c in names], world)
+    mine = [c for c, o in zip(names, owner) if o == rank]
+    dev_inputs, host_inputs = [], []
+    for c in mine:
+        n = cfg['chroms'][c]
+        mats, bias = gen_chrom_device(n, cfg['n_reps'], cfg['dist_max'],
+                                      20261018 + 1000 + 100 * names.index(c),
+                                      cfg['amp'])
+        dev_inputs.append((device_csr(mats, n), bias))
+        host_inputs.append((HostChrom(mats, bias), n))
+    torch.cuda.synchronize()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            td.barrier()
+            torch.cuda.synchronize()
+
+    def step_device():
+        return engine.run_to_qvalues(dev_inputs, design, **kw)
+
+    pinned_out = {}
+
+    def step_e2e():
+        ins = [(device_csr(h.mats, n), h.bias.cuda(non_blocking=True))
+               for h, n in host_inputs]
+        states, dpd, fns, stats = engine.run_to_qvalues(ins, design, **kw)
+        nbytes = 0
+        for i, st in enumerate(states):
+            for k in OUTPUT_NAMES:
+                t = st[k]
+                key = (i, k)
+                if key not in pinned_out or pinned_out[key].shape != t.shape:
+                    pinned_out[key] = torch.empty(
+                        t.shape, dtype=t.dtype).pin_memory()
+                pinned_out[key].copy_(t, non_blocking=True)
+                nbytes += t.numel() * t.element_size()
+        torch.cuda.synchronize()
+        return states, stats, nbytes
+
+    def timed(fn, steps):
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev1 = torch.cuda.Event(enable_timing=True)
+        sync_all()
+        ev0.record()
+        out = None
+        for _ in range(steps):
+            out = fn()
+        ev1.record()
+        sync_all()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device='cuda')
+            td.all_reduce(t, op=td.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, out
+
+    # ---- warm-up, then the device-resident measurement -------------------
+    for _ in range(args.warmup):
+        out = step_device()
+    n_px_local = sum(int(s['row'].numel()) for s in out[0])
+    n_d_local = sum(int(s['disp_index'].numel()) for s in out[0])
+    del out
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    lib().query('h3d_reset_launch_count')
+    ms, out = timed(step_device, args.steps)
+    launches = int(lib().query('h3d_launch_count'))
+    stats = out[3]
+    del out
+    # ---- e2e: host buffers in, host buffers out --------------------------
+    step_e2e()
+    ms_e2e, out_e2e = timed(step_e2e, args.steps)
+    d2h = out_e2e[2]
+    del out_e2e
+    sampler.stop_flag = True
+    sampler.join()
+    h2d = sum(h.nbytes for h, _ in host_inputs)
+
+    tot = torch.tensor([n_px_local, n_d_local, h2d, d2h, launches],
+                       dtype=torch.float64, device='cuda')
+    if world > 1:
+        td.all_reduce(tot)
+    n_px, n_d, h2d_all, d2h_all, launches_all = [float(v) for v in tot.cpu()]
+
+    if rank == 0:
+        peak = ops.fp64_peak_tflops()
+        eq_s = stats['equalize_us'] * 1e-6
+        eq_flops = 2.0 * EQUALIZE_INST_EQ_PER_PX * stats['pixel_equalizations']
+        achieved = eq_flops / eq_s / 1e12 if eq_s > 0 else None
+        cpu = None
+        if not args.no_cpu_baseline:
+            n_cpu, dt_cpu = time_oracle(0)
+            cpu = dict(value=n_cpu / dt_cpu, unit='pixels/s', cores=1,
+                       kind='port', sample=sample_desc())
+        step_ms = ms / args.steps
+        line = dict(
+            metric='pixels/sec through run_to_qvalues',
+            value=n_px / (step_ms * 1e-3), unit='pixels/s', n_gpus=world,
+            steps=args.steps, warmup=args.warmup, ms_per_step=step_ms,
+            higher_is_better=True, scaling='strong', vs_baseline=None,
+            dtype='f64', data='synthetic',
+            config=dict(workload=cfg['desc'], union_pixels=int(n_px),
+                        disp_pixels=int(n_d), n_reps=cfg['n_reps'],
+                        dist_thresh_max=cfg['dist_max'],
+                        sharding='chromosomes dealt to ranks (LPT); '
+                                 'dispersion pooled by distance (all-to-all); '
+                                 'BH all-gather',
+                        l2='inputs (%.1f GB/step) larger than L2'
+                           % (h2d_all / 1e9)),
+            e2e=dict(value=n_px / (ms_e2e / args.steps * 1e-3),
+                     unit='pixels/s', h2d_bytes_per_step=int(h2d_all),
+                     d2h_bytes_per_step=int(d2h_all)),
+            gpu_launches=int(launches_all),
+            roofline=dict(
+                bound='fp64', kernel='equalize_kernel',
+                achieved=achieved, peak=peak, unit='TFLOP/s',
+                frac=(achieved / peak) if achieved and peak else None,
+                traffic=None,
+                model='2 x %.0f FP64 inst-eq per pixel-equalisation '
+                      '(SURVEY 8(d)) x %d pixel-equalisations / %.1f ms of '
+                      'equalize_kernel (CUDA events, %d launches/step, rank 0); '
+                      'peak = FP64 FMA rate measured in this run'
+                      % (EQUALIZE_INST_EQ_PER_PX,
+                         stats['pixel_equalizations'], eq_s * 1e3,
+                         stats['equalize_launches'])),
+            qcml=dict(outer_iterations=stats['outer_iterations'],
+                      nll_evaluations=stats['nll_evaluations'],
+                      nll_ms=stats['nll_us'] * 1e-3,
+                      equalize_ms=stats['equalize_us'] * 1e-3),
+            cpu_baseline=cpu,
+            clocks=sampler.summary())
+        print(json.dumps(line))
+    if world > 1:
+        td.barrier()
+        td.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

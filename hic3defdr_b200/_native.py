@@ -18,6 +18,7 @@ SIGNATURES = {
     'h3d_last_error': (ctypes.c_char_p, []),
     'h3d_launch_count': (ctypes.c_ulonglong, []),
     'h3d_reset_launch_count': (None, []),
+    'h3d_fp64_peak': (c_int, [vp, vp, vp]),
     'h3d_bias_filter': (c_int, [vp, c_int, c_int, c_dbl, vp]),
     'h3d_union_count': (c_int, [c_int, vp, c_int, vp, vp, c_int, vp, c_int,
                                 c_int, vp, vp, c_sz, vp]),

@@ -29,9 +29,8 @@ import pandas as pd
 import scipy.sparse as sparse
 import torch
 
-from hic3defdr_b200 import ops
 from hic3defdr_b200 import dist as hdist
-from hic3defdr_b200.trend import lowess_fit, weighted_lowess_fit
+from hic3defdr_b200 import engine, ops
 
 
 def eprint(*args, **kwargs):
@@ -274,8 +273,9 @@ class HiC3DeFDR(object):
         eprint('preparing data for chrom %s' % chrom)
         eprint('  loading bias', skip=not verbose)
         self._cache.pop(chrom, None)
-        bias = self._bias_device(chrom)
-
+        bias_raw = np.ascontiguousarray(np.array(
+            [_loadtxt(p.replace('<chrom>', chrom))
+             for p in self.bias_patterns]).T)
         eprint('  computing union pixel set', skip=not verbose)
         with ThreadPoolExecutor(self._io_threads(n_threads)) as ex:
             mats = list(ex.map(
@@ -283,41 +283,29 @@ class HiC3DeFDR(object):
                 self.raw_npz_patterns))
         csr = ops.DeviceCSR(mats)
         del mats
-        eprint('  loading raw data', skip=not verbose)
-        eprint('  loading balanced data', skip=not verbose)
-        u = ops.union_gather(csr, self.dist_thresh_max, bias)
-        del csr
-        row, col, dist, raw, data = u['row'], u['col'], u['dist'], u['raw'], \
-            u['balanced']
-
-        eprint('  computing size factors', skip=not verbose)
-        table = ops.size_factor_table(data, dist, self.dist_thresh_max, n_bins,
-                                      norm)
-        eprint('  computing disp_idx', skip=not verbose)
-        scaled, size_factors, disp_idx = ops.scale_filter(
-            row, col, data, table, self._design(), self.dist_thresh_max,
-            self.mean_thresh, self.dist_thresh_min)
-        disp_index = ops.mask_to_index(disp_idx)
-        to_save = []
+        loop_pixels = None
         if self.loop_patterns:
             eprint('  making loop_idx', skip=not verbose)
             loop_pixels = set().union(
                 *sum((load_clusters(pattern.replace('<chrom>', chrom))
                       for pattern in self.loop_patterns.values()), []))
-            loop_idx = ops.loop_membership(row, col, disp_index, loop_pixels)
-            to_save.append((loop_idx.bool(), 'loop_idx', chrom))
+        eprint('  loading raw data', skip=not verbose)
+        eprint('  loading balanced data', skip=not verbose)
+        eprint('  computing size factors', skip=not verbose)
+        eprint('  computing disp_idx', skip=not verbose)
+        st = engine.prepare_chrom(
+            csr, bias_raw, self._design(), self.dist_thresh_min,
+            self.dist_thresh_max, self.bias_thresh, self.mean_thresh, norm,
+            n_bins, loop_pixels)
+        del csr
         eprint('  saving data to disk', skip=not verbose)
-        to_save += [(row, 'row', chrom), (col, 'col', chrom),
-                    (raw, 'raw', chrom),
-                    (size_factors, 'size_factors', chrom),
-                    (scaled, 'scaled', chrom),
-                    (disp_idx.bool(), 'disp_idx', chrom)]
+        to_save = [(st[k].bool() if k in ('disp_idx', 'loop_idx') else st[k],
+                    k, chrom)
+                   for k in ('loop_idx', 'row', 'col', 'raw', 'size_factors',
+                             'scaled', 'disp_idx') if k in st]
         self._save_many(to_save, n_threads)
-        c = self._cache.setdefault(chrom, {})
-        c.update(row=row, col=col, raw=raw, size_factors=size_factors,
-                 disp_idx=disp_idx, disp_index=disp_index)
-        if self.loop_patterns:
-            c['loop_idx'] = loop_idx
+        st.pop('scaled')
+        self._cache[chrom] = st
 
     # ------------------------------------------------------ estimate_disp
     def estimate_disp(self, estimator='qcml', frac=None, auto_frac_factor=15.,
@@ -328,79 +316,24 @@ class HiC3DeFDR(object):
             raise ValueError(
                 "estimator must be one of 'qcml', 'cml', 'mme' on the GPU "
                 "path (python callables cannot run on the device)")
-        lowess_fn = weighted_lowess_fit if weighted_lowess else lowess_fit
-        design = self._design()
-        n_reps, n_conds = design.shape
-        dmax = self.dist_thresh_max
         eprint('  loading data')
         mine = self._my_chroms()
         states = [self._chrom_state(
             c, ['row', 'col', 'raw', 'size_factors', 'disp_idx', 'disp_index',
                 'bias']) for c in mine]
-        counts = [int(s['disp_index'].numel()) for s in states]
-        offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
-        n_tot = int(offs[-1])
-        dist_cat = torch.empty(n_tot, dtype=torch.int32, device='cuda')
-        for s, o, n in zip(states, offs[:-1], counts):
-            if s['size_factors'].dim() != 2:
-                raise IndexError(
-                    'estimate_disp needs per-pixel size factors (a '
-                    'conditional norm), as in the reference '
-                    '(analysis/analysis.py:181)')
-            ops.gather_counts_factors(s['row'], s['col'], s['disp_index'],
-                                      None, None, None, None, n_tot, None,
-                                      None, dist_cat[o:o + n])
-        # pool by distance: stable rank keeps (chromosome, row, col) order
-        # inside every distance, the order of ``raw[dist == d]`` in the
-        # reference (analysis/analysis.py:196-197)
-        rank, key_start = ops.stable_rank(dist_cat, dmax + 1) if n_tot else \
-            (dist_cat, torch.zeros(dmax + 2, dtype=torch.int64))
-        x = torch.empty((n_reps, max(n_tot, 1)), dtype=torch.float64,
-                        device='cuda')
-        f = torch.empty_like(x)
-        for s, o, n in zip(states, offs[:-1], counts):
-            ops.gather_counts_factors(s['row'], s['col'], s['disp_index'],
-                                      s['raw'], s['size_factors'], s['bias'],
-                                      rank[o:o + n], x.shape[1], x, f, None)
-        seg_start = key_start.cpu().numpy()
-        # multi-GPU: regroup so that every distance lives on one rank
-        x, f, seg_start, owner = hdist.exchange_by_distance(
-            x, f, seg_start, n_tot)
-        disp_per_dist, stats = ops.estimate_dispersion(
-            x, f, seg_start, design, estimator)
-        disp_per_dist = hdist.merge_disp_per_dist(disp_per_dist, owner)
+        disp_per_dist, fns, stats = engine.estimate_disp(
+            states, self._design(), self.dist_thresh_max,
+            cond_names=list(self.design.columns), estimator=estimator,
+            frac=frac, auto_frac_factor=auto_frac_factor,
+            weighted_lowess=weighted_lowess, log=eprint)
         self.timings['qcml_stats'] = stats
-        del x, f
-
-        disp = torch.empty((n_tot, n_conds), dtype=torch.float64,
-                           device='cuda')
-        table = np.full((dmax + 1, n_conds), np.nan)
-        for c, cond in enumerate(self.design.columns):
-            eprint('  estimating dispersion for condition %s' % cond)
-            eprint('  fitting distance vs dispersion relationship')
-            idx = np.isfinite(disp_per_dist[:, c])
-            xs = np.arange(dmax + 1)[idx]
-            ys = disp_per_dist[:, c][idx]
-            lowess_kwargs = {'left_boundary': ys[0]}
-            if frac is not None:
-                lowess_kwargs['frac'] = frac
-            if weighted_lowess:
-                lowess_kwargs['auto_frac_factor'] = auto_frac_factor
-            disp_fn = lowess_fn(xs, ys, **lowess_kwargs)
-            table[:, c] = disp_fn(np.arange(dmax + 1))
-            if hdist.rank() == 0:
-                self.save_disp_fn(cond, disp_fn)
-        if n_tot:
-            disp = ops.gather_table(dist_cat, table)
         eprint('  saving estimated dispersions to disk')
-        items = []
-        for i, (c, s) in enumerate(zip(mine, states)):
-            d = disp[offs[i]:offs[i + 1]]
-            self._cache[c]['disp'] = d
-            items.append((d, 'disp', c))
-        self._save_many(items, n_threads)
         if hdist.rank() == 0:
+            for cond, fn in zip(self.design.columns, fns):
+                self.save_disp_fn(cond, fn)
             self.save_data(disp_per_dist, 'disp_per_dist')
+        self._save_many([(s['disp'], 'disp', c)
+                         for c, s in zip(mine, states)], n_threads)
         hdist.barrier()
 
     # ---------------------------------------------------------------- lrt
@@ -418,35 +351,24 @@ class HiC3DeFDR(object):
                                       'disp_index', 'row', 'col', 'raw',
                                       'disp'])
         eprint('  computing LRT results', skip=not verbose)
-        p, llr, mu0, mu1 = ops.lrt_fused(
-            s['row'], s['col'], s['disp_index'], s['raw'], s['size_factors'],
-            s['bias'], s['disp'], self._design(), refit_mu)
+        engine.lrt_chrom(s, self._design(), refit_mu)
         eprint('  saving results to disk', skip=not verbose)
-        self._save_many([(p, 'pvalues', chrom), (llr, 'llr', chrom),
-                         (mu0, 'mu_hat_null', chrom),
-                         (mu1, 'mu_hat_alt', chrom)], n_threads)
-        s['pvalues'] = p
+        self._save_many([(s[k], k, chrom) for k in
+                         ('pvalues', 'llr', 'mu_hat_null', 'mu_hat_alt')],
+                        n_threads)
+        for k in ('llr', 'mu_hat_null', 'mu_hat_alt'):
+            s.pop(k)
 
     # ----------------------------------------------------------------- bh
     def bh(self):
         """analysis/analysis.py:286-303."""
         eprint('applying BH-FDR correction')
         mine = self._my_chroms()
-        ps = []
-        for c in mine:
-            s = self._chrom_state(c, ['pvalues'])
-            p = s['pvalues']
-            if self.loop_patterns:
-                li = self._chrom_state(c, ['loop_idx'])['loop_idx']
-                p = p[li.bool()]
-            ps.append(p)
-        counts = [int(p.numel()) for p in ps]
-        local = torch.cat(ps) if ps else torch.empty(
-            0, dtype=torch.float64, device='cuda')
-        q = hdist.global_bh(local)
-        offs = np.concatenate([[0], np.cumsum(counts)])
-        self._save_many([(q[offs[i]:offs[i + 1]], 'qvalues', c)
-                         for i, c in enumerate(mine)])
+        names = ['pvalues'] + (['loop_idx'] if self.loop_patterns else [])
+        states = [self._chrom_state(c, names) for c in mine]
+        engine.bh(states, use_loop_idx=bool(self.loop_patterns))
+        self._save_many([(s['qvalues'], 'qvalues', c)
+                         for c, s in zip(mine, states)])
         hdist.barrier()
 
     def run_to_qvalues(self, norm='conditional_mor', n_bins_norm=-1,

@@ -21,9 +21,58 @@ void count_launch(int n) { g_launches.fetch_add((unsigned long long)n); }
 
 }  // namespace h3d
 
+namespace h3d {
+
+// register-resident FP64 FMA chains: 8 independent accumulators per thread
+__global__ void __launch_bounds__(256)
+fp64_peak_kernel(double* out, int iters, double a, double b) {
+    double v0 = threadIdx.x * 1e-3, v1 = v0 + 1.0, v2 = v0 + 2.0, v3 = v0 + 3.0;
+    double v4 = v0 + 4.0, v5 = v0 + 5.0, v6 = v0 + 6.0, v7 = v0 + 7.0;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            v0 = fma(v0, a, b); v1 = fma(v1, a, b); v2 = fma(v2, a, b); v3 = fma(v3, a, b);
+            v4 = fma(v4, a, b); v5 = fma(v5, a, b); v6 = fma(v6, a, b); v7 = fma(v7, a, b);
+        }
+    }
+    const double s = ((v0 + v1) + (v2 + v3)) + ((v4 + v5) + (v6 + v7));
+    if (s == 123.456) out[0] = s;      // keeps the chains alive
+}
+
+}  // namespace h3d
+
 extern "C" {
 
 int h3d_version(void) { return 100; }
+
+// Measures the FP64 FMA issue rate of the current device (the roofline
+// denominator of the FP64-bound kernels; MEASURED_PEAKS.json has no FP64
+// entry).  Returns TFLOP/s (FMA = 2 flops) in *tflops_out.  Synchronises.
+int h3d_fp64_peak(double* scratch, double* tflops_out, h3d_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaEvent_t e0, e1;
+    H3D_CHECK(cudaEventCreate(&e0));
+    H3D_CHECK(cudaEventCreate(&e1));
+    const int blocks = h3d::kNumSMs * 8, iters = 4096;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        H3D_CHECK(cudaEventRecord(e0, st));
+        h3d::fp64_peak_kernel<<<blocks, 256, 0, st>>>(scratch, iters, 0.999999, 1e-6);
+        H3D_LAUNCHED("fp64_peak_kernel");
+        H3D_CHECK(cudaEventRecord(e1, st));
+        H3D_CHECK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        H3D_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 64.0 * (double)iters * 256.0 * (double)blocks;
+        const double tf = flops / ((double)ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops_out = best;
+    return H3D_OK;
+}
+
 
 const char* h3d_last_error(void) { return h3d::g_error; }
 

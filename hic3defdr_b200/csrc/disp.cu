@@ -336,7 +336,7 @@ extern "C" int h3d_estimate_dispersion(const double* x, const double* f, long lo
     H3D_REQUIRE(seg_start_host[0] == 0 && n_px <= ld, "segments must start at 0 and fit in ld");
     const int n_prob = n_seg * n_conds;
     for (int p = 0; p < n_prob; ++p) disp_per_dist_host[p] = NAN;
-    if (stats_host) for (int k = 0; k < 4; ++k) stats_host[k] = 0;
+    if (stats_host) for (int k = 0; k < 8; ++k) stats_host[k] = 0;
     if (n_px == 0) return H3D_OK;
 
     // chunk tables (host)
@@ -383,6 +383,12 @@ extern "C" int h3d_estimate_dispersion(const double* x, const double* f, long lo
     H3D_LAUNCHED("init_problems_kernel");
     const dim3 cgrid(n_chunks, n_conds);
     Counters h_cnt;
+    // per-kernel device time of the two heavy kernels (CUDA events on the
+    // launching stream; read after the synchronisation each iteration does)
+    cudaEvent_t ev[4];
+    for (int k = 0; k < 4; ++k) H3D_CHECK(cudaEventCreate(&ev[k]));
+    double eq_us = 0.0, nll_us = 0.0;
+    long long eq_launches = 0, nll_launches = 0;
 
 #define DISPATCH_RC(CALL)                       \
     if (max_rc <= 2) { CALL(2); }               \
@@ -403,21 +409,26 @@ extern "C" int h3d_estimate_dispersion(const double* x, const double* f, long lo
         int guard = 0;
         bool need_eq = true;
         while (true) {
+            const bool did_eq = need_eq;
             if (need_eq) {
+                H3D_CHECK(cudaEventRecord(ev[0], st));
 #define CALL(M) equalize_kernel<M><<<cgrid, 256, 0, st>>>(x, f, ld, chunk_seg, chunk_lo, seg_start, cr, \
         estimator, prob, pseudo, cnt)
                 DISPATCH_RC(CALL)
 #undef CALL
                 H3D_LAUNCHED("equalize_kernel");
+                H3D_CHECK(cudaEventRecord(ev[1], st));
                 step_kernel<<<pgrid, 128, 0, st>>>(prob, seg_chunk_start, partial, partial_cnt, n_chunks,
                                                    n_seg, n_conds, estimator, 0, cnt);
                 H3D_LAUNCHED("step_kernel");
             }
+            H3D_CHECK(cudaEventRecord(ev[2], st));
 #define CALL(M) nll_kernel<M><<<cgrid, 256, 0, st>>>(pseudo, ld, chunk_seg, chunk_lo, seg_start, cr, prob, \
         partial, n_chunks)
             DISPATCH_RC(CALL)
 #undef CALL
             H3D_LAUNCHED("nll_kernel");
+            H3D_CHECK(cudaEventRecord(ev[3], st));
             reset_counters_kernel<<<1, 1, 0, st>>>(cnt);
             H3D_LAUNCHED("reset_counters_kernel");
             step_kernel<<<pgrid, 128, 0, st>>>(prob, seg_chunk_start, partial, partial_cnt, n_chunks, n_seg,
@@ -425,6 +436,15 @@ extern "C" int h3d_estimate_dispersion(const double* x, const double* f, long lo
             H3D_LAUNCHED("step_kernel");
             H3D_CHECK(cudaMemcpyAsync(&h_cnt, cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
             H3D_CHECK(cudaStreamSynchronize(st));
+            {
+                float ms = 0.f;
+                if (did_eq) {
+                    H3D_CHECK(cudaEventElapsedTime(&ms, ev[0], ev[1]));
+                    eq_us += 1e3 * (double)ms; ++eq_launches;
+                }
+                H3D_CHECK(cudaEventElapsedTime(&ms, ev[2], ev[3]));
+                nll_us += 1e3 * (double)ms; ++nll_launches;
+            }
             if (h_cnt.n_failed > 0) {
                 set_error("bounded Brent search failed for %d (distance, condition) bins "
                           "(NaN likelihood or evaluation budget exhausted)", h_cnt.n_failed);
@@ -440,6 +460,7 @@ extern "C" int h3d_estimate_dispersion(const double* x, const double* f, long lo
             if (++guard > 100000) { set_error("qCML did not terminate"); return H3D_ERR_NUMERIC; }
         }
     }
+    for (int k = 0; k < 4; ++k) cudaEventDestroy(ev[k]);
     collect_kernel<<<1, 256, 0, st>>>(prob, n_prob, disp_dev, stats_dev);
     H3D_LAUNCHED("collect_kernel");
     H3D_CHECK(cudaMemcpyAsync(disp_per_dist_host, disp_dev, (size_t)n_prob * 8, cudaMemcpyDeviceToHost, st));
@@ -449,6 +470,8 @@ extern "C" int h3d_estimate_dispersion(const double* x, const double* f, long lo
     if (stats_host) {
         stats_host[0] = h_stats[0]; stats_host[1] = h_stats[1]; stats_host[2] = h_stats[2];
         stats_host[3] = (long long)(h3d_launch_count() - launches_before);
+        stats_host[4] = eq_launches; stats_host[5] = (long long)eq_us;
+        stats_host[6] = nll_launches; stats_host[7] = (long long)nll_us;
     }
     return H3D_OK;
 }

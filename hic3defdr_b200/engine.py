@@ -1,0 +1,187 @@
+"""
+Device-resident stages of ``run_to_qvalues``: the orchestration shared by the
+drop-in class (hic3defdr_b200/analysis.py, which adds the file I/O) and by
+bench.py (which times it with inputs already in HBM).  Each function takes
+and returns CUDA tensors; the arithmetic is in libh3d (include/h3d.h).
+
+A chromosome's state is a dict of tensors named after the reference's files
+(hic3defdr/analysis/analysis.py:125-133, 219-223, 281-284, 302-303):
+row, col, raw, size_factors, scaled, disp_idx (+ disp_index, the positions of
+the True entries), bias, [loop_idx], disp, pvalues, llr, mu_hat_null,
+mu_hat_alt, qvalues.
+"""
+import numpy as np
+import torch
+
+from hic3defdr_b200 import dist as hdist
+from hic3defdr_b200 import ops
+from hic3defdr_b200.trend import lowess_fit, weighted_lowess_fit
+
+
+def prepare_chrom(csr, bias_raw, design, dist_min=4, dist_max=200,
+                  bias_thresh=0.1, mean_thresh=1.0, norm='conditional_mor',
+                  n_bins=-1, loop_pixels=None):
+    """hic3defdr/analysis/analysis.py:63-133 for one chromosome.
+    ``csr``: ops.DeviceCSR; ``bias_raw``: (n_bins, R) unfiltered bias."""
+    if n_bins == -1:
+        n_bins = int(dist_max / 5)
+    bias = ops.filter_bias(bias_raw, bias_thresh)
+    u = ops.union_gather(csr, dist_max, bias)
+    st = dict(bias=bias, row=u['row'], col=u['col'], raw=u['raw'])
+    if u['row'].numel() == 0:
+        r = csr.n_reps
+        st.update(size_factors=torch.empty((0, r), dtype=torch.float64,
+                                           device='cuda'),
+                  scaled=u['balanced'],
+                  disp_idx=torch.empty(0, dtype=torch.uint8, device='cuda'),
+                  disp_index=torch.empty(0, dtype=torch.int32, device='cuda'))
+        return st
+    table = ops.size_factor_table(u['balanced'], u['dist'], dist_max, n_bins,
+                                  norm)
+    scaled, sf, disp_idx = ops.scale_filter(
+        u['row'], u['col'], u['balanced'], table, design, dist_max,
+        mean_thresh, dist_min)
+    st.update(size_factors=sf, scaled=scaled, disp_idx=disp_idx,
+              disp_index=ops.mask_to_index(disp_idx))
+    if loop_pixels is not None:
+        st['loop_idx'] = ops.loop_membership(st['row'], st['col'],
+                                             st['disp_index'], loop_pixels)
+    return st
+
+
+def pool_by_distance(states, dist_max):
+    """Pools the disp_idx pixels of the given chromosomes by distance
+    (analysis/analysis.py:169-183, 196-197): returns (x, f) SoA (R, n) in
+    (distance, chromosome, row, col) order, the per-pixel distances in
+    chromosome order, the segment boundaries (host int64) and the
+    per-chromosome offsets."""
+    counts = [int(s['disp_index'].numel()) for s in states]
+    offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    n_tot = int(offs[-1])
+    n_reps = states[0]['raw'].shape[1] if states else 1
+    dist_cat = torch.empty(n_tot, dtype=torch.int32, device='cuda')
+    for s, o, n in zip(states, offs[:-1], counts):
+        if s['size_factors'].dim() != 2:
+            raise IndexError(
+                'estimate_disp needs per-pixel size factors (a conditional '
+                'norm), as in the reference (analysis/analysis.py:181)')
+        if n:
+            ops.gather_counts_factors(s['row'], s['col'], s['disp_index'],
+                                      None, None, None, None, n_tot, None,
+                                      None, dist_cat[o:o + n])
+    x = torch.empty((n_reps, max(n_tot, 1)), dtype=torch.float64,
+                    device='cuda')
+    f = torch.empty_like(x)
+    if n_tot:
+        rank, key_start = ops.stable_rank(dist_cat, dist_max + 1)
+        for s, o, n in zip(states, offs[:-1], counts):
+            if n:
+                ops.gather_counts_factors(
+                    s['row'], s['col'], s['disp_index'], s['raw'],
+                    s['size_factors'], s['bias'], rank[o:o + n], x.shape[1],
+                    x, f, None)
+        seg_start = key_start.cpu().numpy()
+    else:
+        seg_start = np.zeros(dist_max + 2, dtype=np.int64)
+    return x, f, dist_cat, seg_start, offs
+
+
+def fit_trends(disp_per_dist, dist_max, cond_names, frac=None,
+               auto_frac_factor=15., weighted_lowess=True, log=None):
+    """analysis/analysis.py:208-218: one trend per condition; returns
+    (list of callables, (dist_max + 1, C) table of their values)."""
+    lowess_fn = weighted_lowess_fit if weighted_lowess else lowess_fit
+    n_conds = disp_per_dist.shape[1]
+    table = np.full((dist_max + 1, n_conds), np.nan)
+    fns = []
+    for c in range(n_conds):
+        if log:
+            log('  estimating dispersion for condition %s' % cond_names[c])
+            log('  fitting distance vs dispersion relationship')
+        idx = np.isfinite(disp_per_dist[:, c])
+        xs = np.arange(dist_max + 1)[idx]
+        ys = disp_per_dist[:, c][idx]
+        kwargs = {'left_boundary': ys[0]}
+        if frac is not None:
+            kwargs['frac'] = frac
+        if weighted_lowess:
+            kwargs['auto_frac_factor'] = auto_frac_factor
+        fn = lowess_fn(xs, ys, **kwargs)
+        table[:, c] = fn(np.arange(dist_max + 1))
+        fns.append(fn)
+    return fns, table
+
+
+def estimate_disp(states, design, dist_max, cond_names=None, estimator='qcml',
+                  frac=None, auto_frac_factor=15., weighted_lowess=True,
+                  log=None):
+    """analysis/analysis.py:163-223 on device states (this rank's
+    chromosomes).  Sets ``disp`` in every state; returns
+    (disp_per_dist (D+1, C) numpy, list of trend callables, stats)."""
+    n_conds = design.shape[1]
+    if cond_names is None:
+        cond_names = [str(c) for c in range(n_conds)]
+    x, f, dist_cat, seg_start, offs = pool_by_distance(states, dist_max)
+    n_tot = int(offs[-1])
+    # multi-GPU: every distance is estimated on the rank that owns it
+    x, f, seg_start, owner = hdist.exchange_by_distance(x, f, seg_start, n_tot)
+    disp_per_dist, stats = ops.estimate_dispersion(x, f, seg_start, design,
+                                                   estimator)
+    disp_per_dist = hdist.merge_disp_per_dist(disp_per_dist, owner)
+    del x, f
+    fns, table = fit_trends(disp_per_dist, dist_max, cond_names, frac,
+                            auto_frac_factor, weighted_lowess, log)
+    disp = ops.gather_table(dist_cat, table) if n_tot else torch.empty(
+        (0, n_conds), dtype=torch.float64, device='cuda')
+    for i, s in enumerate(states):
+        s['disp'] = disp[offs[i]:offs[i + 1]]
+    return disp_per_dist, fns, stats
+
+
+def lrt_chrom(st, design, refit_mu=True):
+    """analysis/analysis.py:261-284 for one chromosome state."""
+    p, llr, mu0, mu1 = ops.lrt_fused(
+        st['row'], st['col'], st['disp_index'], st['raw'], st['size_factors'],
+        st['bias'], st['disp'], design, refit_mu)
+    st.update(pvalues=p, llr=llr, mu_hat_null=mu0, mu_hat_alt=mu1)
+    return st
+
+
+def bh(states, use_loop_idx=False):
+    """analysis/analysis.py:295-303 over this rank's chromosome states (and,
+    through hic3defdr_b200.dist, every other rank's)."""
+    ps = []
+    for s in states:
+        p = s['pvalues']
+        if use_loop_idx:
+            p = p[s['loop_idx'].bool()]
+        ps.append(p)
+    counts = [int(p.numel()) for p in ps]
+    local = torch.cat(ps) if ps else torch.empty(0, dtype=torch.float64,
+                                                 device='cuda')
+    q = hdist.global_bh(local)
+    offs = np.concatenate([[0], np.cumsum(counts)])
+    for i, s in enumerate(states):
+        s['qvalues'] = q[offs[i]:offs[i + 1]]
+    return states
+
+
+def run_to_qvalues(chrom_inputs, design, dist_min=4, dist_max=200,
+                   bias_thresh=0.1, mean_thresh=1.0, norm='conditional_mor',
+                   n_bins=-1, estimator='qcml', frac=None,
+                   auto_frac_factor=15., weighted_lowess=True, refit_mu=True):
+    """All four steps on device inputs: ``chrom_inputs`` is a list of
+    (ops.DeviceCSR, bias_raw CUDA tensor) for THIS rank's chromosomes.
+    Returns (states, disp_per_dist, trend callables, qcml stats)."""
+    design = np.asarray(design).astype(bool)
+    states = [prepare_chrom(csr, b, design, dist_min, dist_max, bias_thresh,
+                            mean_thresh, norm, n_bins)
+              for csr, b in chrom_inputs]
+    dpd, fns, stats = estimate_disp(states, design, dist_max,
+                                    estimator=estimator, frac=frac,
+                                    auto_frac_factor=auto_frac_factor,
+                                    weighted_lowess=weighted_lowess)
+    for s in states:
+        lrt_chrom(s, design, refit_mu)
+    bh(states)
+    return states, dpd, fns, stats

@@ -59,6 +59,14 @@ def _check_failed(counter, what):
 # prepare_data
 # --------------------------------------------------------------------------
 
+def fp64_peak_tflops():
+    """Measured FP64 FMA rate of the current device (TFLOP/s, FMA = 2)."""
+    scratch = torch.zeros(8, dtype=torch.float64, device='cuda')
+    out = np.zeros(1)
+    lib().call('h3d_fp64_peak', ptr(scratch), ptr(out), _stream())
+    return float(out[0])
+
+
 def filter_bias(bias, bias_thresh):
     """hic3defdr/analysis/core.py:58-59 on an (n_bins, n_reps) matrix."""
     b = dev(bias, torch.float64).clone()
@@ -280,7 +288,7 @@ def estimate_dispersion(x_soa, f_soa, seg_start, design, estimator='qcml'):
     n_seg = len(seg) - 1
     ld = x_soa.shape[1]
     out = np.empty((n_seg, n_conds))
-    stats = np.zeros(4, dtype=np.int64)
+    stats = np.zeros(8, dtype=np.int64)
     wsb = lib().query('h3d_estimate_dispersion_ws_bytes', int(seg[-1]), n_seg,
                       n_reps, n_conds)
     ws = workspace(wsb)
@@ -292,7 +300,10 @@ def estimate_dispersion(x_soa, f_soa, seg_start, design, estimator='qcml'):
     return out, dict(outer_iterations=int(stats[0]),
                      nll_evaluations=int(stats[1]),
                      pixel_equalizations=int(stats[2]),
-                     launches=int(stats[3]))
+                     launches=int(stats[3]),
+                     equalize_launches=int(stats[4]),
+                     equalize_us=int(stats[5]),
+                     nll_launches=int(stats[6]), nll_us=int(stats[7]))
 
 
 def _single_bin(data, f, estimator):

@@ -59,6 +59,10 @@ const char* h3d_last_error(void);
 /* number of kernels this library has launched since load / last reset */
 unsigned long long h3d_launch_count(void);
 void h3d_reset_launch_count(void);
+/* measured FP64 FMA rate of the current device in TFLOP/s (FMA = 2 flops):
+ * the roofline denominator of the FP64-bound kernels.  scratch: >= 8 bytes on
+ * the device; tflops_out: HOST.  Synchronises. */
+int h3d_fp64_peak(double* scratch, double* tflops_out_host, h3d_stream_t stream);
 
 /* ---- prepare_data ------------------------------------------------------ */
 
@@ -153,8 +157,9 @@ size_t h3d_stable_rank_ws_bytes(long long n, int n_keys);
  * (util/scaled_nb.py:186-275).  x, f: SoA (n_reps, ld) pooled by distance
  * (segment d = [seg_start_host[d], seg_start_host[d + 1])).
  * disp_per_dist_host: (n_seg, n_conds) HOST output, NaN for empty segments.
- * stats_host (may be NULL): 4 int64 = {outer iterations, NLL evaluations,
- * pixel-equalisations, kernel launches}.  Synchronises. */
+ * stats_host (may be NULL): 8 int64 = {outer iterations, NLL evaluations,
+ * pixel-equalisations, kernel launches, equalize launches, equalize time (us,
+ * CUDA events on ``stream``), NLL launches, NLL time (us)}.  Synchronises. */
 #define H3D_EST_QCML 0
 #define H3D_EST_CML 1
 #define H3D_EST_MME 2

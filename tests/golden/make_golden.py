@@ -135,6 +135,39 @@ def pipeline(Ref):
     for cond in ('A', 'B'):
         out['disp_fn_%s' % cond] = h.load_disp_fn(cond)(xs.copy())
     out['design'] = kw['design'].values
+    # the reference's own reproducibility floor for disp_per_dist: its qCML
+    # result under random permutations of the pixel order inside each bin
+    # (summation order changes the Brent path)
+    import warnings
+    from hic3defdr.util.dispersion import qcml as ref_qcml
+    design = kw['design'].values.astype(bool)
+    raws, fs, dists = [], [], []
+    for chrom in CHROMS:
+        di = out['disp_idx_%s' % chrom]
+        bias = h.load_bias(chrom)
+        r, c = out['row_%s' % chrom][di], out['col_%s' % chrom][di]
+        raws.append(out['raw_%s' % chrom][di])
+        fs.append(bias[r] * bias[c] * out['size_factors_%s' % chrom][di])
+        dists.append(c - r)
+    raw, f, dist = np.concatenate(raws), np.concatenate(fs), \
+        np.concatenate(dists)
+    rng = np.random.default_rng(2026)
+    noise = np.zeros_like(out['disp_per_dist'])
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        for d in range(DIST_MAX + 1):
+            sel = dist == d
+            if not sel.any():
+                continue
+            for ci in range(design.shape[1]):
+                x, ff = raw[sel][:, design[:, ci]], f[sel][:, design[:, ci]]
+                base = ref_qcml(x, f=ff.copy())
+                assert base == out['disp_per_dist'][d, ci]
+                for _ in range(4):
+                    perm = rng.permutation(len(x))
+                    v = ref_qcml(x[perm], f=ff[perm].copy())
+                    noise[d, ci] = max(noise[d, ci], abs(v - base) / base)
+    out['disp_selfnoise'] = noise
     out['meta'] = np.array([DIST_MAX, N_REPS, 4])
     shutil.rmtree(root)
     return out

@@ -66,7 +66,12 @@ def test_pooled_estimate_vs_recorded_reference():
     want = g['disp_per_dist']
     assert np.array_equal(np.isnan(got), np.isnan(want))
     ok = np.isfinite(want)
-    np.testing.assert_allclose(got[ok], want[ok], rtol=DISP_RTOL)
+    # bar: within max(1e-7, 3x the reference's own permutation self-noise of
+    # that bin, recorded in the fixture); these bins hold only ~450 pixels
+    tol = np.maximum(DISP_RTOL, 3 * g['disp_selfnoise'])
+    assert g['disp_selfnoise'].max() < 5e-6
+    assert (np.abs(got[ok] - want[ok]) <= tol[ok] * want[ok]).all(), \
+        np.max(np.abs(got[ok] - want[ok]) / want[ok])
     assert stats['outer_iterations'] >= ok.sum()
     # the other estimators against the oracle on the same pooled data
     for est, fn in (('mme', op.mme),):
