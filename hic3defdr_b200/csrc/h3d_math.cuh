@@ -23,6 +23,15 @@
 #define H3D_HDN inline
 #endif
 
+// optional host-side instrumentation (tests/hostcheck only)
+#ifdef H3D_HOST_STATS
+struct H3dStats { long long n_tail_eval, n_series_it, n_cf_it, n_q2q; };
+extern H3dStats g_h3d_stats;
+#define H3D_STAT(field) (++g_h3d_stats.field)
+#else
+#define H3D_STAT(field) ((void)0)
+#endif
+
 namespace h3d {
 
 constexpr int kMaxReps = 16;
@@ -125,6 +134,7 @@ H3D_HD double gamma_p_series(double a, double x, double lga) {
     if (ax < -745.2) return 0.0;
     double r = a, c = 1.0, ans = 1.0;
     for (int i = 0; i < 20000; ++i) {
+        H3D_STAT(n_series_it);
         r += 1.0;
         c *= x / r;
         ans += c;
@@ -144,6 +154,7 @@ H3D_HD double gamma_q_cf(double a, double x, double lga) {
     double d = 1.0 / bb;
     double h = d;
     for (int i = 1; i < 20000; ++i) {
+        H3D_STAT(n_cf_it);
         const double an = -(double)i * ((double)i - a);
         bb += 2.0;
         d = an * d + bb;
@@ -201,8 +212,9 @@ H3D_HD double gamma_tail_inv(double a, double t, double lga, bool upper,
         if (ys < 0.2 * (a + 1.0)) y = ys;
     }
     if (!(y > 0.0)) y = 1.0;
-    for (int it = 0; it < 200; ++it) {
+    for (int it = 0; it < 100; ++it) {
         const double T = gamma_tail(a, y, lga, upper);
+        H3D_STAT(n_tail_eval);
         if (T == t) return y;
         // bracket update: upper tail decreases in y, lower tail increases
         const bool y_too_small = upper ? (T > t) : (T < t);
@@ -218,17 +230,18 @@ H3D_HD double gamma_tail_inv(double a, double t, double lga, bool upper,
                 // log P is close to linear in log y
                 nxt = y * exp(-(lT - lt) / (y * exp(lpdf - lT)));
             }
+            // quadratic convergence: a step this small means nxt is converged
+            // to round-off (the next correction would be ~1e-18 relative)
+            if (fabs(nxt - y) <= 1e-9 * fabs(nxt)) return nxt;
         }
-        const bool inside = (nxt > lo) && (nxt < hi);
-        if (!inside) {
-            // fall back on the bracket: bisect (geometrically when possible),
-            // or expand while one side is still open
+        if (!((nxt > lo) && (nxt < hi))) {
+            // Newton left the bracket (or was not available): bisect
+            // (geometrically when possible), or expand an open side
             if (isinf(hi)) nxt = (lo > 0.0) ? lo * 2.0 : 1.0;
             else if (lo == 0.0) nxt = hi * 0.25;
             else nxt = sqrt(lo) * sqrt(hi);
+            if ((hi - lo) <= 4.0 * kEps * hi) return nxt;
         }
-        if (fabs(nxt - y) <= 2.0 * kEps * fabs(nxt)) return nxt;
-        if (!isinf(hi) && (hi - lo) <= 2.0 * kEps * hi) return nxt;
         y = nxt;
     }
     return y;

@@ -1,7 +1,9 @@
 // TEST TOOL: compiles the scalar FP64 building blocks of
 // hic3defdr_b200/csrc/h3d_math.cuh as HOST code so that their algorithms can be
 // checked against scipy on a machine without a GPU.  Never used by the product.
+#define H3D_HOST_STATS
 #include "../../hic3defdr_b200/csrc/h3d_math.cuh"
+H3dStats g_h3d_stats = {0, 0, 0, 0};
 extern "C" {
 void hc_fit_mu(const double* x, const double* b, const double* alpha, int n, int R,
                double* out, int* status) {
@@ -29,6 +31,11 @@ void hc_q2q(const double* x, const double* mu_in, const double* mu_out, double a
 }
 void hc_chi2_sf(const double* x, int n, int df, double* out) {
     for (int i = 0; i < n; ++i) out[i] = h3d::chi2_sf(x[i], df);
+}
+void hc_stats(long long* out, int reset) {
+    out[0] = g_h3d_stats.n_tail_eval; out[1] = g_h3d_stats.n_series_it;
+    out[2] = g_h3d_stats.n_cf_it; out[3] = g_h3d_stats.n_q2q;
+    if (reset) g_h3d_stats = H3dStats{0, 0, 0, 0};
 }
 // drives the Brent state machine with a callback
 typedef double (*hc_fn)(double);
