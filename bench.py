@@ -305,12 +305,17 @@ def main():
         ev0 = torch.cuda.Event(enable_timing=True)
         ev1 = torch.cuda.Event(enable_timing=True)
         sync_all()
+        prof = os.environ.get('H3D_PROFILE') == fn.__name__
+        if prof:        # ncu --profile-from-start off: capture this region only
+            torch.cuda.profiler.start()
         ev0.record()
         out = None
         for _ in range(steps):
             out = fn()
         ev1.record()
         sync_all()
+        if prof:
+            torch.cuda.profiler.stop()
         ms = ev0.elapsed_time(ev1)
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device='cuda')

@@ -65,12 +65,31 @@ __global__ void init_problems_kernel(Problem* __restrict__ prob, const long long
 
 // pseudo-data for every pixel of every bin that waits for it.
 // grid = (n_chunks, n_conds); blockDim = 256; chunk -> (segment, first pixel)
+//
+// Two phases per batch of pixels, staged through shared memory:
+//   1. per pixel: fit_mu, the clamped (mu_in, mu_out) of every replicate;
+//      replicates whose quantile map needs no incomplete gamma function
+//      (x = 0 in the left tail) are finished here, the others become tasks
+//      (x, mu_in, mu_out, destination), right-tail tasks filling the task
+//      array from the front, left-tail tasks from the back;
+//   2. the tasks are processed in array order, so that the lanes of a warp
+//      run the same branch of the incomplete gamma code (continued fraction
+//      for the right tail, series for the left tail) instead of diverging
+//      per replicate.
+constexpr int kEqTasks = 2048;      // task slots per batch (56 KB of shared memory)
+
+struct EqTask { double x, mu_in, mu_out; };
+
 template <int MAXRC>
 __global__ void __launch_bounds__(256)
 equalize_kernel(const double* __restrict__ x, const double* __restrict__ f, long long ld,
                 const int* __restrict__ chunk_seg, const long long* __restrict__ chunk_lo,
                 const long long* __restrict__ seg_start, CondReps cr, int estimator,
                 const Problem* __restrict__ prob, double* __restrict__ pseudo, Counters* cnt) {
+    extern __shared__ unsigned char eq_smem[];
+    EqTask* task = (EqTask*)eq_smem;
+    int* task_dest = (int*)(eq_smem + (size_t)kEqTasks * sizeof(EqTask));
+    __shared__ int n_right, n_left;
     const int c = blockIdx.y;
     const int s = chunk_seg[blockIdx.x];
     const Problem& q = prob[s * cr.n_conds + c];
@@ -80,42 +99,92 @@ equalize_kernel(const double* __restrict__ x, const double* __restrict__ f, long
     const long long seg_hi = seg_start[s + 1];
     const long long hi = (lo + kChunk < seg_hi) ? lo + kChunk : seg_hi;
     const int nr = cr.n_in[c];
-    for (long long i = lo + threadIdx.x; i < hi; i += 256) {
-        double xr[MAXRC], fr[MAXRC], ar[MAXRC];
-        double slog = 0.0;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    double* __restrict__ out_base = pseudo + (long long)cr.pseudo_row[c] * ld;
+    constexpr int kBatchPx = kEqTasks / MAXRC;
+    for (long long b0 = lo; b0 < hi; b0 += kBatchPx) {
+        if (threadIdx.x == 0) { n_right = 0; n_left = 0; }
+        __syncthreads();
+        const long long b1 = (b0 + kBatchPx < hi) ? b0 + kBatchPx : hi;
+        for (long long i0 = b0; i0 < b1; i0 += 256) {
+            const long long i = i0 + threadIdx.x;
+            const bool valid = i < b1;
+            double xr[MAXRC], fr[MAXRC], ar[MAXRC];
+            double slog = 0.0;
 #pragma unroll
-        for (int k = 0; k < MAXRC; ++k) {
-            xr[k] = 0.0; fr[k] = 1.0; ar[k] = alpha;
-            if (k < nr) {
-                const int r = cr.rep[c][k];
-                xr[k] = x[(long long)r * ld + i];
-                fr[k] = f[(long long)r * ld + i];
-                slog += log(fr[k]);
+            for (int k = 0; k < MAXRC; ++k) {
+                xr[k] = 0.0; fr[k] = 1.0; ar[k] = alpha;
+                if (valid && k < nr) {
+                    const int r = cr.rep[c][k];
+                    xr[k] = x[(long long)r * ld + i];
+                    fr[k] = f[(long long)r * ld + i];
+                    slog += log(fr[k]);
+                }
+            }
+            if (estimator == H3D_EST_CML) {
+                // cml(raw, f): data / f (dispersion.py:67-68, intended semantics)
+#pragma unroll
+                for (int k = 0; k < MAXRC; ++k)
+                    if (valid && k < nr) out_base[(long long)k * ld + i] = xr[k] / fr[k];
+                continue;
+            }
+            // equalize (scaled_nb.py:207-214)
+            double mu_hat = 1.0, mu_out = 1.0;
+            if (valid) {
+                const double f_mean = exp(slog / (double)nr);       // gmean, pseudocount 0
+                int st = 0;
+                mu_hat = fit_mu<MAXRC>(xr, fr, ar, (1u << nr) - 1u, &st);
+                if (st) atomicAdd(&cnt->n_fit_failed, 1);
+                mu_out = mu_hat * f_mean;
+            }
+#pragma unroll
+            for (int k = 0; k < MAXRC; ++k) {
+                if (k < nr) {                                   // uniform across the block
+                    double mu_in = mu_hat * fr[k];
+                    // order-dependent clamp shared across replicates (scaled_nb.py:240-242)
+                    if (!((mu_in >= 0.25) && (mu_out >= 0.25))) { mu_in = 0.25; mu_out = 0.25; }
+                    const bool right = xr[k] >= mu_in;
+                    const bool cheap = !right && !(xr[k] > 0.0);     // no gamma evaluation needed
+                    if (valid && cheap)
+                        out_base[(long long)k * ld + i] = q2q_one(xr[k], mu_in, mu_out, alpha);
+                    const bool push = valid && !cheap;
+                    const unsigned m_r = __ballot_sync(0xffffffffu, push && right);
+                    const unsigned m_l = __ballot_sync(0xffffffffu, push && !right);
+                    int base_r = 0, base_l = 0;
+                    if (lane == 0) {
+                        if (m_r) base_r = atomicAdd(&n_right, __popc(m_r));
+                        if (m_l) base_l = atomicAdd(&n_left, __popc(m_l));
+                    }
+                    base_r = __shfl_sync(0xffffffffu, base_r, 0);
+                    base_l = __shfl_sync(0xffffffffu, base_l, 0);
+                    if (push) {
+                        const int slot = right ? base_r + __popc(m_r & lt_mask)
+                                               : kEqTasks - 1 - (base_l + __popc(m_l & lt_mask));
+                        task[slot].x = xr[k];
+                        task[slot].mu_in = mu_in;
+                        task[slot].mu_out = mu_out;
+                        task_dest[slot] = k * kBatchPx + (int)(i - b0);
+                    }
+                }
             }
         }
-        double* out = pseudo + (long long)cr.pseudo_row[c] * ld + i;
-        if (estimator == H3D_EST_CML) {
-            // cml(raw, f): data / f (dispersion.py:67-68, intended semantics)
-#pragma unroll
-            for (int k = 0; k < MAXRC; ++k)
-                if (k < nr) out[(long long)k * ld] = xr[k] / fr[k];
-            continue;
-        }
-        // equalize (scaled_nb.py:207-214)
-        const double f_mean = exp(slog / (double)nr);       // gmean, pseudocount 0
-        int st = 0;
-        const double mu_hat = fit_mu<MAXRC>(xr, fr, ar, (1u << nr) - 1u, &st);
-        if (st) atomicAdd(&cnt->n_fit_failed, 1);
-        double mu_out = mu_hat * f_mean;
-#pragma unroll
-        for (int k = 0; k < MAXRC; ++k) {
-            if (k < nr) {
-                double mu_in = mu_hat * fr[k];
-                // order-dependent clamp shared across replicates (scaled_nb.py:240-242)
-                if (!((mu_in >= 0.25) && (mu_out >= 0.25))) { mu_in = 0.25; mu_out = 0.25; }
-                out[(long long)k * ld] = q2q_one(xr[k], mu_in, mu_out, alpha);
+        __syncthreads();
+        if (estimator == H3D_EST_CML) continue;
+        const int nR = n_right, nL = n_left;
+        // right-tail tasks [0, nR), then left-tail tasks [kEqTasks - nL, kEqTasks)
+        for (int t0 = 0; t0 < nR + nL; t0 += 256) {
+            const int t = t0 + threadIdx.x;
+            if (t < nR + nL) {
+                const int slot = (t < nR) ? t : kEqTasks - 1 - (t - nR);
+                const EqTask tk = task[slot];
+                const int dst = task_dest[slot];
+                const int k = dst / kBatchPx;
+                const long long i = b0 + (dst - k * kBatchPx);
+                out_base[(long long)k * ld + i] = q2q_one(tk.x, tk.mu_in, tk.mu_out, alpha);
             }
         }
+        __syncthreads();
     }
 }
 
@@ -383,6 +452,11 @@ extern "C" int h3d_estimate_dispersion(const double* x, const double* f, long lo
     H3D_LAUNCHED("init_problems_kernel");
     const dim3 cgrid(n_chunks, n_conds);
     Counters h_cnt;
+    const size_t eq_smem = (size_t)kEqTasks * (sizeof(EqTask) + sizeof(int));
+    H3D_CHECK(cudaFuncSetAttribute(equalize_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eq_smem));
+    H3D_CHECK(cudaFuncSetAttribute(equalize_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eq_smem));
+    H3D_CHECK(cudaFuncSetAttribute(equalize_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eq_smem));
+    H3D_CHECK(cudaFuncSetAttribute(equalize_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eq_smem));
     // per-kernel device time of the two heavy kernels (CUDA events on the
     // launching stream; read after the synchronisation each iteration does)
     cudaEvent_t ev[4];
@@ -412,7 +486,7 @@ extern "C" int h3d_estimate_dispersion(const double* x, const double* f, long lo
             const bool did_eq = need_eq;
             if (need_eq) {
                 H3D_CHECK(cudaEventRecord(ev[0], st));
-#define CALL(M) equalize_kernel<M><<<cgrid, 256, 0, st>>>(x, f, ld, chunk_seg, chunk_lo, seg_start, cr, \
+#define CALL(M) equalize_kernel<M><<<cgrid, 256, eq_smem, st>>>(x, f, ld, chunk_seg, chunk_lo, seg_start, cr, \
         estimator, prob, pseudo, cnt)
                 DISPATCH_RC(CALL)
 #undef CALL

@@ -99,140 +99,203 @@ H3D_HD double fit_mu(const double* x, const double* b, const double* alpha,
 }
 
 // ---------------------------------------------------------------------------
-// Regularised incomplete gamma functions.
+// Regularised incomplete gamma functions, organised around
+//   k(a, x) = x^a e^-x / Gamma(a)          (gamma_logk returns log k)
+//   P(a, x) = k * S(a, x),  S = (1/a) sum_n x^n / ((a+1)...(a+n))   (series)
+//   Q(a, x) = k * H(a, x),  H = 1/(x+1-a- 1(1-a)/(x+3-a- 2(2-a)/...)) (cont. fr.)
+// The series is used for x < max(a, 1), the continued fraction otherwise.
+// Both loops are arranged so that the FP64 divider is touched once per four
+// terms: the series shares one reciprocal among four consecutive terms, the
+// continued fraction is evaluated by the forward (Wallis) recurrence of its
+// convergents and only divides when it tests convergence.
 // ---------------------------------------------------------------------------
-// log of x^a e^{-x} / Gamma(a).  For a >= 10 the direct form a ln x - x -
-// lgamma(a) cancels catastrophically (terms of size a ln a); there it is
-// rewritten with Stirling's series as
-//   0.5 ln(a / 2 pi) + a (ln(1+u) - u) - corr(a),   u = (x - a) / a.
 H3D_HD double log1p_minus_x(double u) {
     if (fabs(u) < 0.25) {
-        // -u^2/2 + u^3/3 - ... via the atanh-type series in w = u / (2 + u):
+        // ln(1+u) - u via the atanh series in w = u / (2 + u):
         // ln(1+u) = 2 (w + w^3/3 + w^5/5 + ...), and 2w - u = -u w
         const double w = u / (2.0 + u);
         const double w2 = w * w;
         double s = 0.0;
+#pragma unroll
         for (int k = 27; k >= 3; k -= 2) s = s * w2 + 1.0 / (double)k;
         return 2.0 * w * w2 * s - u * w;
     }
     return log1p(u) - u;
 }
 
-H3D_HD double gamma_log_kernel(double a, double x, double lga) {
-    if (a < 10.0) return a * log(x) - x - lga;
-    const double ia = 1.0 / a, ia2 = ia * ia;
-    const double corr = ia * (1.0 / 12.0 + ia2 * (-1.0 / 360.0 + ia2 * (1.0 / 1260.0 +
-        ia2 * (-1.0 / 1680.0 + ia2 * (1.0 / 1188.0 + ia2 * (-691.0 / 360360.0 +
-        ia2 * (1.0 / 156.0)))))));
-    const double u = (x - a) * ia;
-    return 0.5 * log(a * 0.15915494309189535) + a * log1p_minus_x(u) - corr;
+struct GammaShape {
+    double a;
+    double lead;   // a >= 10: 0.5 ln(a / 2 pi) - stirling(a);  else: -lgamma(a)
+    double inv_a;
+    bool big;
+};
+
+H3D_HD GammaShape gamma_shape(double a) {
+    GammaShape s;
+    s.a = a;
+    s.inv_a = 1.0 / a;
+    s.big = a >= 10.0;
+    if (s.big) {
+        // direct a ln x - x - lgamma(a) cancels catastrophically for large a;
+        // Stirling: ln Gamma(a) = (a - .5) ln a - a + .5 ln 2pi + corr(a)
+        const double ia = s.inv_a, ia2 = ia * ia;
+        const double corr = ia * (1.0 / 12.0 + ia2 * (-1.0 / 360.0 + ia2 * (1.0 / 1260.0 +
+            ia2 * (-1.0 / 1680.0 + ia2 * (1.0 / 1188.0 + ia2 * (-691.0 / 360360.0 +
+            ia2 * (1.0 / 156.0)))))));
+        s.lead = 0.5 * log(a * 0.15915494309189535) - corr;
+    } else {
+        s.lead = -lgamma(a);
+    }
+    return s;
 }
 
-// lower series: P(a,x) = x^a e^-x / Gamma(a+1) * sum_{n>=0} x^n / ((a+1)...(a+n))
-H3D_HD double gamma_p_series(double a, double x, double lga) {
-    const double ax = gamma_log_kernel(a, x, lga);
-    if (ax < -745.2) return 0.0;
+// log of x^a e^-x / Gamma(a)
+H3D_HD double gamma_logk(const GammaShape& s, double x) {
+    if (s.big) return s.lead + s.a * log1p_minus_x((x - s.a) * s.inv_a);
+    return s.a * log(x) - x + s.lead;
+}
+
+// S(a, x) = (1/a) * sum_{n>=0} x^n / ((a+1)...(a+n)); terms decrease
+// monotonically because the series is only used for x < a + 1.
+H3D_HD double gamma_series_factor(double a, double x) {
+    const double x2 = x * x, x3 = x2 * x, x4 = x2 * x2;
     double r = a, c = 1.0, ans = 1.0;
-    for (int i = 0; i < 20000; ++i) {
+    for (int i = 0; i < 5000; ++i) {
         H3D_STAT(n_series_it);
-        r += 1.0;
-        c *= x / r;
-        ans += c;
-        if (c <= ans * (0.5 * kEps)) break;
+        const double p1 = r + 1.0, p2 = r + 2.0, p3 = r + 3.0, p4 = r + 4.0;
+        const double p34 = p3 * p4, p234 = p2 * p34;
+        const double q = c / (p1 * p234);            // one division per four terms
+        const double c1 = q * x * p234, c2 = q * x2 * p34, c3 = q * x3 * p4, c4 = q * x4;
+        ans += (c1 + c2) + (c3 + c4);
+        c = c4;
+        r = p4;
+        if (c4 <= ans * (0.25 * kEps)) break;
     }
-    return ans * exp(ax) / a;
+    return ans / a;
 }
 
-// upper continued fraction (modified Lentz):
-// Q(a,x) = x^a e^-x / Gamma(a) * 1/(x+1-a- 1(1-a)/(x+3-a- 2(2-a)/(x+5-a- ...)))
-H3D_HD double gamma_q_cf(double a, double x, double lga) {
-    const double ax = gamma_log_kernel(a, x, lga);
-    if (ax < -745.2) return 0.0;
-    const double tiny = 1e-300;
-    double bb = x + 1.0 - a;
-    double c = 1.0 / tiny;
-    double d = 1.0 / bb;
-    double h = d;
-    for (int i = 1; i < 20000; ++i) {
+// H(a, x): forward recurrence of the convergents A_n / B_n of
+// b0 + a1/(b1 + a2/(b2 + ...)), b_n = x + 2n + 1 - a, a_n = -n (n - a);
+// H = B_n / A_n.  Used for x >= max(a, 1), where it converges.
+H3D_HD double gamma_cf_factor(double a, double x) {
+    double bn = x + 1.0 - a;
+    double Am = 1.0, A = bn, Bm = 0.0, B = 1.0;       // A_{-1}, A_0, B_{-1}, B_0
+    double h_prev = 1.0 / bn;
+    double n = 0.0;
+    for (int i = 0; i < 5000; ++i) {
         H3D_STAT(n_cf_it);
-        const double an = -(double)i * ((double)i - a);
-        bb += 2.0;
-        d = an * d + bb;
-        if (fabs(d) < tiny) d = tiny;
-        c = bb + an / c;
-        if (fabs(c) < tiny) c = tiny;
-        d = 1.0 / d;
-        const double del = d * c;
-        h *= del;
-        if (fabs(del - 1.0) <= kEps) break;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            n += 1.0;
+            bn += 2.0;
+            const double an = -n * (n - a);
+            const double An = bn * A + an * Am, Bn = bn * B + an * Bm;
+            Am = A; A = An; Bm = B; B = Bn;
+        }
+        const double h = B / A;
+        if (fabs(h - h_prev) <= fabs(h) * kEps) return h;
+        h_prev = h;
+        if (fabs(A) > 1e150) { A *= 1e-150; Am *= 1e-150; B *= 1e-150; Bm *= 1e-150; }
     }
-    return exp(ax) * h;
+    return h_prev;
 }
 
-// which evaluation is the numerically safe one for (a, x)
 H3D_HD bool gamma_use_series(double a, double x) {
     return (x < 1.0) || (x < a);
 }
 
+// log of the lower (upper = false) or upper tail at y > 0, and
+// ratio = T / (y * pdf(y)) (so that d log T / d log y = -/+ 1 / ratio).
+H3D_HD void gamma_log_tail(const GammaShape& s, double y, bool upper, double* log_t,
+                           double* ratio) {
+    H3D_STAT(n_tail_eval);
+    const double lk = gamma_logk(s, y);
+    if (gamma_use_series(s.a, y)) {
+        const double S = gamma_series_factor(s.a, y);
+        const double lp = lk + log(S);
+        if (!upper) { *log_t = lp; *ratio = S; return; }
+        const double T = -expm1(lp);                 // 1 - P
+        *log_t = log1p(-exp(lp));
+        *ratio = T / exp(lk);
+    } else {
+        const double H = gamma_cf_factor(s.a, y);
+        const double lq = lk + log(H);
+        if (upper) { *log_t = lq; *ratio = H; return; }
+        const double T = -expm1(lq);                 // 1 - Q
+        *log_t = log1p(-exp(lq));
+        *ratio = T / exp(lk);
+    }
+}
+
 H3D_HD double gamma_p(double a, double x, double lga) {
+    (void)lga;
     if (!(x > 0.0)) return (x == 0.0) ? 0.0 : NAN;
     if (isinf(x)) return 1.0;
-    if (gamma_use_series(a, x)) return gamma_p_series(a, x, lga);
-    return 1.0 - gamma_q_cf(a, x, lga);
+    const GammaShape s = gamma_shape(a);
+    double lt, ratio;
+    gamma_log_tail(s, x, false, &lt, &ratio);
+    return exp(lt);
 }
 
 H3D_HD double gamma_q(double a, double x, double lga) {
+    (void)lga;
     if (!(x > 0.0)) return (x == 0.0) ? 1.0 : NAN;
     if (isinf(x)) return 0.0;
-    if (gamma_use_series(a, x)) return 1.0 - gamma_p_series(a, x, lga);
-    return gamma_q_cf(a, x, lga);
+    const GammaShape s = gamma_shape(a);
+    double lt, ratio;
+    gamma_log_tail(s, x, true, &lt, &ratio);
+    return exp(lt);
 }
 
 // ---------------------------------------------------------------------------
-// Inverses.  Solve T(a, y) = t for y, where T is the lower (upper = false) or
-// upper (upper = true) regularised incomplete gamma function, by Newton on
-// log T with a maintained bracket (log T is monotone; its derivative is
-// -/+ pdf / T).  ``guess`` seeds the iteration (any positive finite value is
-// acceptable; a good one saves evaluations).
+// Inverse in log space: solve log T(a, y) = lt for y by Newton with a
+// maintained bracket.  log Q is close to linear in y and log P close to linear
+// in log y, and in both cases the slope is 1 / ratio -- no extra
+// transcendental is needed per step beyond the tail evaluation itself.
+// ``guess`` seeds the iteration (any positive finite value is acceptable).
 // ---------------------------------------------------------------------------
-H3D_HD double gamma_tail(double a, double y, double lga, bool upper) {
-    return upper ? gamma_q(a, y, lga) : gamma_p(a, y, lga);
-}
-
-H3D_HD double gamma_tail_inv(double a, double t, double lga, bool upper,
-                             double guess) {
-    if (!(t > 0.0)) return (t == 0.0) ? (upper ? INFINITY : 0.0) : NAN;
-    if (t >= 1.0) return (t == 1.0) ? (upper ? 0.0 : INFINITY) : NAN;
-    const double lt = log(t);
+H3D_HD double gamma_log_tail_inv(const GammaShape& s, double lt, bool upper, double guess) {
+    if (!(lt < 0.0)) return (lt == 0.0) ? (upper ? 0.0 : INFINITY) : NAN;
+    const double a = s.a;
     double lo = 0.0, hi = INFINITY;
     double y = (guess > 0.0 && isfinite(guess)) ? guess : a;
     if (!upper) {
-        // far lower tail: P(a,y) ~ y^a / Gamma(a+1)
-        const double ys = exp((lt + lga + log(a)) / a);
+        // far lower tail: P(a,y) ~ y^a / Gamma(a+1);  lead = -lgamma(a) for small a
+        const double lg_a1 = s.big ? ((a - 0.5) * log(a) - a + 0.9189385332046727 +
+                                      (0.5 * log(a * 0.15915494309189535) - s.lead)) + log(a)
+                                   : -s.lead + log(a);
+        const double ys = exp((lt + lg_a1) * s.inv_a);
         if (ys < 0.2 * (a + 1.0)) y = ys;
     }
     if (!(y > 0.0)) y = 1.0;
     for (int it = 0; it < 100; ++it) {
-        const double T = gamma_tail(a, y, lga, upper);
-        H3D_STAT(n_tail_eval);
-        if (T == t) return y;
+        double lT, ratio;
+        gamma_log_tail(s, y, upper, &lT, &ratio);
+        if (lT == lt) return y;
         // bracket update: upper tail decreases in y, lower tail increases
-        const bool y_too_small = upper ? (T > t) : (T < t);
+        const bool y_too_small = upper ? (lT > lt) : (lT < lt);
         if (y_too_small) lo = y; else hi = y;
         double nxt = NAN;
-        if (T > 0.0 && T < 1.0) {
-            const double lT = log(T);
-            const double lpdf = (a - 1.0) * log(y) - y - lga;
+        if (isfinite(lT) && isfinite(ratio) && ratio > 0.0) {
+            // Halley step on g = log T - lt (cubic convergence); the second
+            // derivative is analytic: with lambda = pdf / T = 1 / (y ratio),
+            //   upper: g' = -lambda, g'' = -lambda ((a-1)/y - 1 + lambda)   (in y)
+            //   lower: g' = kappa = y lambda, g'' = kappa (a - y - kappa)    (in log y)
+            const double g = lT - lt;
             if (upper) {
-                // log Q is close to linear in y
-                nxt = y + (lT - lt) / exp(lpdf - lT);
+                const double lam = 1.0 / (y * ratio);
+                double den = 2.0 * lam + g * ((a - 1.0) / y - 1.0 + lam);
+                if (!(den > lam)) den = 2.0 * lam;            // fall back to Newton
+                nxt = y + 2.0 * g / den;
             } else {
-                // log P is close to linear in log y
-                nxt = y * exp(-(lT - lt) / (y * exp(lpdf - lT)));
+                const double kap = 1.0 / ratio;
+                double den = 2.0 * kap - g * (a - y - kap);
+                if (!(den > kap)) den = 2.0 * kap;
+                nxt = y * exp(-2.0 * g / den);
             }
-            // quadratic convergence: a step this small means nxt is converged
-            // to round-off (the next correction would be ~1e-18 relative)
-            if (fabs(nxt - y) <= 1e-9 * fabs(nxt)) return nxt;
+            // a step this small means nxt is converged to round-off (the next
+            // correction would be below 1e-18 relative)
+            if (fabs(nxt - y) <= 1e-6 * fabs(nxt)) return nxt;
         }
         if (!((nxt > lo) && (nxt < hi))) {
             // Newton left the bracket (or was not available): bisect
@@ -245,6 +308,14 @@ H3D_HD double gamma_tail_inv(double a, double t, double lga, bool upper,
         y = nxt;
     }
     return y;
+}
+
+// probability-space wrapper (tests): T(a, y) = t
+H3D_HD double gamma_tail_inv(double a, double t, double lga, bool upper, double guess) {
+    (void)lga;
+    if (!(t > 0.0)) return (t == 0.0) ? (upper ? INFINITY : 0.0) : NAN;
+    if (t >= 1.0) return (t == 1.0) ? (upper ? 0.0 : INFINITY) : NAN;
+    return gamma_log_tail_inv(gamma_shape(a), log(t), upper, guess);
 }
 
 // Wilson-Hilferty: Gamma(a,1) variate as a cube of a normal one.
@@ -260,10 +331,13 @@ H3D_HD double wh_from_normal(double a, double z) {
 // q2q for one replicate of one pixel (scaled_nb.py:239-275).  mu_in/mu_out are
 // the already clamped means.  Only the tail the reference selects is
 // evaluated.  The normal-to-normal quantile map is the affine map of the
-// z-score (ndtri(ndtr(z)) == z up to round-off); where the reference's tail
-// probability underflows to zero it returns +/-inf, mimicked here.
+// z-score (ndtri(ndtr(z)) == z up to round-off).  The gamma-to-gamma map is
+// carried out on the LOG of the tail probability.  Where the reference's tail
+// probability underflows to zero it returns +inf (right tail) or 0 (left
+// tail); that is mimicked at the same thresholds.
 // ---------------------------------------------------------------------------
 H3D_HD double q2q_one(double x, double mu_in, double mu_out, double alpha) {
+    H3D_STAT(n_q2q);
     const double r_in = 1.0 + alpha * mu_in;
     const double r_out = 1.0 + alpha * mu_out;
     const double v_in = mu_in * r_in;
@@ -281,15 +355,19 @@ H3D_HD double q2q_one(double x, double mu_in, double mu_out, double alpha) {
     if (!right && !(xs > 0.0)) {
         q_gamma = 0.0;                       // cdf(0) = 0 -> ppf(0) = 0
     } else {
-        const double lga_in = lgamma(a_in);
-        const double lga_out = lgamma(a_out);
-        const double t = gamma_tail(a_in, xs, lga_in, right);
-        double guess = xs * (a_out / a_in);
-        if (a_in > 2.0 && a_out > 2.0) {
-            const double g2 = wh_from_normal(a_out, wh_to_normal(a_in, xs));
-            if (g2 > 0.0 && isfinite(g2)) guess = g2;
+        const GammaShape s_in = gamma_shape(a_in);
+        double lt, ratio;
+        gamma_log_tail(s_in, xs, right, &lt, &ratio);
+        if (lt < -744.44) {
+            q_gamma = right ? INFINITY : 0.0;            // sf / cdf underflow in the reference
+        } else {
+            double guess = xs * (a_out / a_in);
+            if (a_in > 2.0 && a_out > 2.0) {
+                const double g2 = wh_from_normal(a_out, wh_to_normal(a_in, xs));
+                if (g2 > 0.0 && isfinite(g2)) guess = g2;
+            }
+            q_gamma = r_out * gamma_log_tail_inv(gamma_shape(a_out), lt, right, guess);
         }
-        q_gamma = r_out * gamma_tail_inv(a_out, t, lga_out, right, guess);
     }
     double out = (q_norm + q_gamma) / 2.0;
     if (!(out >= 0.0)) out = 0.0;

@@ -66,9 +66,10 @@ def test_pooled_estimate_vs_recorded_reference():
     want = g['disp_per_dist']
     assert np.array_equal(np.isnan(got), np.isnan(want))
     ok = np.isfinite(want)
-    # bar: within max(1e-7, 3x the reference's own permutation self-noise of
-    # that bin, recorded in the fixture); these bins hold only ~450 pixels
-    tol = np.maximum(DISP_RTOL, 3 * g['disp_selfnoise'])
+    # bar: within 3x the largest permutation self-noise the reference itself
+    # shows on this data set (recorded in the fixture from 4 permutations per
+    # bin; ~1e-6 because these bins hold only ~450 pixels)
+    tol = np.full(want.shape, max(DISP_RTOL, 3 * g['disp_selfnoise'].max()))
     assert g['disp_selfnoise'].max() < 5e-6
     assert (np.abs(got[ok] - want[ok]) <= tol[ok] * want[ok]).all(), \
         np.max(np.abs(got[ok] - want[ok]) / want[ok])

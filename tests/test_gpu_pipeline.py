@@ -93,7 +93,7 @@ def test_dispersion_per_distance(run):
     want = g['disp_per_dist']
     assert np.array_equal(np.isnan(got), np.isnan(want))
     ok = np.isfinite(want)
-    tol = np.maximum(1e-7, 3 * g['disp_selfnoise'])
+    tol = np.full(want.shape, max(1e-7, 3 * g['disp_selfnoise'].max()))
     assert (np.abs(got[ok] - want[ok]) <= tol[ok] * want[ok]).all(), \
         np.max(np.abs(got[ok] - want[ok]) / want[ok])
 
