@@ -151,7 +151,13 @@ H3D_HD GammaShape gamma_shape(double a) {
 
 // log of x^a e^-x / Gamma(a)
 H3D_HD double gamma_logk(const GammaShape& s, double x) {
-    if (s.big) return s.lead + s.a * log1p_minus_x((x - s.a) * s.inv_a);
+    if (s.big) {
+        const double u = (x - s.a) * s.inv_a;
+        // away from u = 0 take the log of x / a itself: log1p(u) would inherit
+        // the rounding of u, amplified by 1 / (1 + u) in the far left tail
+        const double l = (fabs(u) < 0.25) ? log1p_minus_x(u) : log(x * s.inv_a) - u;
+        return s.lead + s.a * l;
+    }
     return s.a * log(x) - x + s.lead;
 }
 
@@ -346,7 +352,9 @@ H3D_HD double q2q_one(double x, double mu_in, double mu_out, double alpha) {
     // normal part
     const double z = (x - mu_in) / sqrt(v_in);
     double q_norm;
-    if (fabs(z) > 38.4674056) q_norm = right ? INFINITY : -INFINITY;  // ndtr underflow
+    // scipy's ndtr goes through cephes erfc, which flushes to zero once
+    // z^2 / 2 exceeds MAXLOG = 709.78...; isf(0) / ppf(0) are then +/-inf
+    if (0.5 * z * z > 709.782712893384) q_norm = right ? INFINITY : -INFINITY;
     else q_norm = mu_out + sqrt(v_out) * z;
     // gamma part
     const double a_in = mu_in / r_in, a_out = mu_out / r_out;
@@ -358,7 +366,9 @@ H3D_HD double q2q_one(double x, double mu_in, double mu_out, double alpha) {
         const GammaShape s_in = gamma_shape(a_in);
         double lt, ratio;
         gamma_log_tail(s_in, xs, right, &lt, &ratio);
-        if (lt < -744.44) {
+        // cephes igam/igamc flush to zero when the kernel x^a e^-x / Gamma(a)
+        // underflows exp(-MAXLOG); ratio > 0 keeps log(kernel) = lt - log(ratio)
+        if (lt - log(ratio) < -709.782712893384 || lt < -744.44) {
             q_gamma = right ? INFINITY : 0.0;            // sf / cdf underflow in the reference
         } else {
             double guess = xs * (a_out / a_in);

@@ -1,0 +1,113 @@
+"""CPU, world_size 2, gloo: the host-side logic of the multi-GPU path
+(hic3defdr_b200/dist.py): chromosome sharding, the distance all-to-all with
+receiver-side regrouping, the merge of per-distance results and the global
+BH gather.  The CUDA kernels are not involved (the arithmetic callbacks are
+replaced by numpy stand-ins where the product would call libh3d)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as td
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, ret):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    td.init_process_group('gloo', rank=rank, world_size=world)
+    from hic3defdr_b200 import dist as hd
+    from oracle import pipeline as op
+    try:
+        # 1. sharding is a partition, identical on every rank
+        chroms = ['c%d' % i for i in range(7)]
+        w = {c: (i * 37) % 11 + 1 for i, c in enumerate(chroms)}
+        mine = hd.shard_chroms(chroms, lambda c: w[c])
+        gathered = [None] * world
+        td.all_gather_object(gathered, mine)
+        assert sorted(sum(gathered, [])) == sorted(chroms)
+        # 2. exchange by distance: every pixel ends on the owner of its
+        # distance, grouped by distance, source ranks in rank order
+        rng = np.random.default_rng(100 + rank)
+        n_dist, n_reps, n = 12, 3, 200 + 50 * rank
+        dist = np.sort(rng.integers(2, n_dist, size=n))
+        seg = np.concatenate([[0], np.cumsum(np.bincount(dist, minlength=n_dist))])
+        x = np.stack([dist * 1000.0 + rank * 100 + r for r in range(n_reps)])
+        ident = rng.random(n)                       # per-pixel tag
+        f = np.stack([ident + r for r in range(n_reps)])
+        xo, fo, seg_o, bounds = hd.exchange_by_distance(
+            torch.from_numpy(x), torch.from_numpy(f), seg, n)
+        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+        n_got = int(seg_o[-1])
+        xo, fo = xo.numpy()[:, :n_got], fo.numpy()[:, :n_got]
+        for d in range(n_dist):
+            a, b = int(seg_o[d]), int(seg_o[d + 1])
+            if not (lo <= d < hi):
+                assert a == b
+                continue
+            assert (xo[0, a:b] // 1000 == d).all()
+            src = (xo[0, a:b] % 1000) // 100
+            assert (np.diff(src) >= 0).all()        # rank order inside a distance
+        # every pixel arrived exactly once, on exactly one rank
+        tags = [None] * world
+        td.all_gather_object(tags, fo[0].tolist())
+        sent = [None] * world
+        td.all_gather_object(sent, ident.tolist())
+        assert sorted(sum(tags, [])) == sorted(sum(sent, []))
+        # 3. merge of per-distance dispersions
+        local = np.full((n_dist, 2), np.nan)
+        local[lo:hi] = np.arange(lo, hi)[:, None] + np.array([0.0, 0.5])
+        local[lo:hi][seg_o[lo + 1:hi + 1] - seg_o[lo:hi] == 0] = np.nan
+        merged = hd.merge_disp_per_dist(local, bounds)
+        counts = np.zeros(n_dist)
+        allc = [None] * world
+        td.all_gather_object(allc, np.bincount(dist, minlength=n_dist).tolist())
+        counts = np.sum(allc, axis=0)
+        assert np.array_equal(np.isnan(merged[:, 0]), counts == 0)
+        ok = counts > 0
+        assert np.array_equal(merged[ok, 1], np.arange(n_dist)[ok] + 0.5)
+        # 4. global BH equals BH over the concatenation
+        p_local = rng.random(300 + 17 * rank) ** 2
+        q_local = hd.global_bh(torch.from_numpy(p_local),
+                               bh_fn=lambda t: torch.from_numpy(op.bh(t.numpy())))
+        allp = [None] * world
+        td.all_gather_object(allp, p_local.tolist())
+        q_all = op.bh(np.concatenate([np.array(v) for v in allp]))
+        start = sum(len(v) for v in allp[:rank])
+        assert np.array_equal(q_local.numpy(), q_all[start:start + len(p_local)])
+        ret[rank] = 'ok'
+    except Exception as e:          # surface the failure in the parent
+        import traceback
+        ret[rank] = traceback.format_exc()
+    finally:
+        td.destroy_process_group()
+
+
+def test_two_rank_host_logic():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    for r in range(world):
+        assert ret.get(r) == 'ok', ret.get(r)
+
+
+def test_lpt_and_ranges():
+    from hic3defdr_b200 import dist as hd
+    owner = hd.lpt_assign([10, 9, 8, 7, 1, 1], 2)
+    loads = [sum(w for w, o in zip([10, 9, 8, 7, 1, 1], owner) if o == k)
+             for k in range(2)]
+    assert abs(loads[0] - loads[1]) <= 2
+    b = hd.distance_ranges(np.array([0, 0, 5, 5, 5, 5, 0]), 2)
+    assert b[0] == 0 and b[-1] == 7 and b[1] in (4, 5)
+    b = hd.distance_ranges(np.zeros(5, dtype=int), 3)
+    assert (np.diff(b) >= 0).all() and b[-1] == 5

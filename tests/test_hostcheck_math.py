@@ -1,0 +1,126 @@
+"""CPU checks of the scalar FP64 building blocks in
+hic3defdr_b200/csrc/h3d_math.cuh, compiled as host code by
+tests/hostcheck/hostcheck.cpp (a test tool, never used by the product):
+incomplete gamma pair and inverses vs scipy, q2q vs the oracle, fit_mu vs the
+oracle, the Brent state machine vs scipy's bounded minimiser."""
+import ctypes
+import os
+import subprocess
+import warnings
+
+import numpy as np
+import pytest
+import scipy.special as sp
+from scipy.optimize import minimize_scalar
+
+from oracle import pipeline as op
+from tests.helpers import load_stage_golden
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, 'hostcheck', 'hostcheck.cpp')
+LIB = os.path.join(HERE, 'hostcheck', 'libhostcheck.so')
+dp = ctypes.POINTER(ctypes.c_double)
+
+
+def P(a):
+    return a.ctypes.data_as(dp)
+
+
+@pytest.fixture(scope='module')
+def L():
+    hdr = os.path.join(os.path.dirname(HERE), 'hic3defdr_b200', 'csrc',
+                       'h3d_math.cuh')
+    if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(
+            os.path.getmtime(SRC), os.path.getmtime(hdr)):
+        subprocess.run(['g++', '-O2', '-shared', '-fPIC', '-o', LIB, SRC,
+                        '-lm'], check=True)
+    lib = ctypes.CDLL(LIB)
+    lib.hc_brent.restype = ctypes.c_double
+    return lib
+
+
+def test_incomplete_gamma_pair(L):
+    rng = np.random.default_rng(1)
+    n = 100000
+    a = 10 ** rng.uniform(-1, 3, n)
+    x = a * 10 ** rng.normal(0, 0.5, n)
+    x[:1000] = a[:1000] * (1 + rng.normal(0, 0.01, 1000))
+    p, q = np.zeros(n), np.zeros(n)
+    L.hc_gamma_pq(P(a), P(x), n, P(p), P(q))
+    pr, qr = sp.gammainc(a, x), sp.gammaincc(a, x)
+    small = np.where(pr < qr, np.abs(p - pr) / np.maximum(pr, 1e-300),
+                     np.abs(q - qr) / np.maximum(qr, 1e-300))
+    ok = np.minimum(pr, qr) > 1e-290
+    # scipy itself is only good to ~1e-11 for a ~ 1e3 (checked with mpmath)
+    assert small[ok].max() < 5e-11
+    # values down to 1e-290: exponents of ~700 carry ~1e-13 in both codes
+    assert small[ok & (a < 100)].max() < 1e-12
+
+
+@pytest.mark.parametrize('upper', [0, 1])
+def test_incomplete_gamma_inverse(L, upper):
+    rng = np.random.default_rng(2 + upper)
+    n = 100000
+    a = 10 ** rng.uniform(-1, 3, n)
+    t = 10 ** rng.uniform(-30, -0.01, n)
+    y = np.zeros(n)
+    L.hc_gamma_inv(P(a), P(t), n, upper, P(y))
+    yr = sp.gammainccinv(a, t) if upper else sp.gammaincinv(a, t)
+    m = np.isfinite(yr) & (yr > 1e-290)
+    assert (np.abs(y[m] - yr[m]) / yr[m]).max() < 2e-12
+
+
+@pytest.mark.parametrize('alpha', [0.01, 0.0005, 0.3])
+def test_q2q_vs_oracle(L, alpha):
+    rng = np.random.default_rng(3)
+    n = 100000
+    mu_in = 10 ** rng.uniform(-1.2, 2.7, n)
+    mu_out = mu_in * np.exp(rng.normal(0, 0.3, n))
+    x = rng.poisson(rng.gamma(1 / alpha, mu_in * alpha)).astype(float)
+    x[:100] = 0
+    x[100:200] = np.round(mu_in[100:200] * 8 + 20)
+    mi, mo = mu_in.copy(), mu_out.copy()
+    ref = op.q2q(x, mi, mo, alpha)          # clamps mi / mo in place
+    out = np.zeros(n)
+    L.hc_q2q(P(x), P(mi), P(mo), ctypes.c_double(alpha), n, P(out))
+    assert np.array_equal(np.isfinite(out), np.isfinite(ref))
+    m = np.isfinite(ref)
+    # relative to max(value, 1e-3): tiny outputs are cancellation residues
+    assert (np.abs(out[m] - ref[m]) / np.maximum(ref[m], 1e-3)).max() < 1e-11
+
+
+def test_fit_mu_vs_oracle(L):
+    rng = np.random.default_rng(4)
+    n, R = 50000, 4
+    b = rng.lognormal(0, 0.4, (n, R))
+    mu = 10 ** rng.uniform(-1, 3, n)
+    alpha = 10 ** rng.uniform(-3, 0.5, (n, R))
+    x = rng.poisson(rng.gamma(1 / alpha, mu[:, None] * b * alpha)).astype(float)
+    keep = x.sum(1) > 0
+    x, b, alpha = x[keep], b[keep], alpha[keep]
+    n = len(x)
+    out = np.zeros(n)
+    st = np.zeros(n, dtype=np.int32)
+    L.hc_fit_mu(P(x), P(b), P(alpha), n, R, P(out),
+                st.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
+    assert (st == 0).all()
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        ref = op.fit_mu_hat(x, b, alpha)
+    assert (np.abs(out - ref) / ref).max() < 1e-10
+    g = np.sum((x - out[:, None] * b) /
+               (out[:, None] + alpha * out[:, None] ** 2 * b), axis=1)
+    assert np.abs(g).max() < 1e-12      # tighter than the reference's 1e-5
+
+
+def test_brent_state_machine_matches_scipy(L):
+    s = load_stage_golden()
+    CB = ctypes.CFUNCTYPE(ctypes.c_double, ctypes.c_double)
+    for data in (s['equalize_0.01'], s['equalize_0.2'], s['equalize4_0.05']):
+        f = lambda t: float(op.cml_nll(data, t))
+        res = minimize_scalar(f, bounds=(1e-4, 100. / 101), method='bounded')
+        nfev, flag = ctypes.c_int(), ctypes.c_int()
+        xf = L.hc_brent(CB(f), ctypes.c_double(1e-4),
+                        ctypes.c_double(100. / 101), ctypes.c_double(1e-5),
+                        500, ctypes.byref(nfev), ctypes.byref(flag))
+        assert xf == res.x and nfev.value == res.nfev and flag.value == 0
