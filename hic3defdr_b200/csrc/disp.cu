@@ -147,7 +147,7 @@ equalize_kernel(const double* __restrict__ x, const double* __restrict__ f, long
                     const bool right = xr[k] >= mu_in;
                     const bool cheap = !right && !(xr[k] > 0.0);     // no gamma evaluation needed
                     if (valid && cheap)
-                        out_base[(long long)k * ld + i] = q2q_one(xr[k], mu_in, mu_out, alpha);
+                        out_base[(long long)k * ld + i] = q2q_zero(mu_in, mu_out, alpha);
                     const bool push = valid && !cheap;
                     const unsigned m_r = __ballot_sync(0xffffffffu, push && right);
                     const unsigned m_l = __ballot_sync(0xffffffffu, push && !right);
@@ -215,7 +215,7 @@ nll_kernel(const double* __restrict__ pseudo, long long ld, const int* __restric
     const double r = 1.0 / delta - 1.0;
     const int nr = cr.n_in[c];
     const double nrr = (double)nr * r;
-    const double cst = lgamma(nrr) - (double)nr * lgamma(r);
+    const double cst = lgamma_pos(nrr) - (double)nr * lgamma_pos(r);
     const long long lo = chunk_lo[blockIdx.x];
     const long long seg_hi = seg_start[s + 1];
     const long long hi = (lo + kChunk < seg_hi) ? lo + kChunk : seg_hi;
@@ -228,10 +228,10 @@ nll_kernel(const double* __restrict__ pseudo, long long ld, const int* __restric
             if (k < nr) {
                 const double y = base[(long long)k * ld + i];
                 z += y;
-                lg += lgamma(y + r);
+                lg += lgamma_pos(y + r);
             }
         }
-        acc += (lg + cst) - lgamma(z + nrr);
+        acc += (lg + cst) - lgamma_pos(z + nrr);
     }
     const double tot = block_sum_256(acc, sh);
     if (threadIdx.x == 0) partial[(long long)c * n_chunks + blockIdx.x] = tot;

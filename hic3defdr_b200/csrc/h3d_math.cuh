@@ -17,10 +17,10 @@
 
 #ifdef __CUDACC__
 #define H3D_HD __host__ __device__ __forceinline__
-#define H3D_HDN __host__ __device__ __noinline__
+#define H3D_HDN static __host__ __device__ __noinline__
 #else
 #define H3D_HD inline
-#define H3D_HDN inline
+#define H3D_HDN static inline
 #endif
 
 // optional host-side instrumentation (tests/hostcheck only)
@@ -130,7 +130,7 @@ struct GammaShape {
     bool big;
 };
 
-H3D_HD GammaShape gamma_shape(double a) {
+H3D_HDN GammaShape gamma_shape(double a) {
     GammaShape s;
     s.a = a;
     s.inv_a = 1.0 / a;
@@ -212,8 +212,10 @@ H3D_HD bool gamma_use_series(double a, double x) {
 
 // log of the lower (upper = false) or upper tail at y > 0, and
 // ratio = T / (y * pdf(y)) (so that d log T / d log y = -/+ 1 / ratio).
-H3D_HD void gamma_log_tail(const GammaShape& s, double y, bool upper, double* log_t,
-                           double* ratio) {
+// (not inlined on purpose: one copy of the series / continued-fraction code per
+// kernel keeps the hot loop inside the instruction cache)
+H3D_HDN void gamma_log_tail(const GammaShape& s, double y, bool upper, double* log_t,
+                            double* ratio) {
     H3D_STAT(n_tail_eval);
     const double lk = gamma_logk(s, y);
     if (gamma_use_series(s.a, y)) {
@@ -342,6 +344,19 @@ H3D_HD double wh_from_normal(double a, double z) {
 // probability underflows to zero it returns +inf (right tail) or 0 (left
 // tail); that is mimicked at the same thresholds.
 // ---------------------------------------------------------------------------
+// the x = 0, left-tail case: the gamma quantile map is exactly 0 (cdf(0) = 0
+// -> ppf(0) = 0), only the normal map contributes
+H3D_HD double q2q_zero(double mu_in, double mu_out, double alpha) {
+    const double v_in = mu_in * (1.0 + alpha * mu_in);
+    const double v_out = mu_out * (1.0 + alpha * mu_out);
+    const double z = (0.0 - mu_in) / sqrt(v_in);
+    double q_norm = mu_out + sqrt(v_out) * z;
+    if (0.5 * z * z > 709.782712893384) q_norm = -INFINITY;
+    double out = (q_norm + 0.0) / 2.0;
+    if (!(out >= 0.0)) out = 0.0;
+    return out;
+}
+
 H3D_HD double q2q_one(double x, double mu_in, double mu_out, double alpha) {
     H3D_STAT(n_q2q);
     const double r_in = 1.0 + alpha * mu_in;
@@ -382,6 +397,29 @@ H3D_HD double q2q_one(double x, double mu_in, double mu_out, double alpha) {
     double out = (q_norm + q_gamma) / 2.0;
     if (!(out >= 0.0)) out = 0.0;
     return out;
+}
+
+// ---------------------------------------------------------------------------
+// log Gamma(x) for x > 0 (the only case the conditional NB likelihood needs,
+// dispersion.py:72-75): Stirling's series for x >= 10, the recurrence
+// Gamma(x) = Gamma(x + n) / (x (x+1) ... (x+n-1)) below.  One log (two below
+// 10) and one reciprocal instead of the general-purpose library routine.
+// ---------------------------------------------------------------------------
+H3D_HD double lgamma_pos(double x) {
+    double shift = 0.0;
+    if (x < 10.0) {
+        double p = 1.0;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+            if (x < 10.0) { p *= x; x += 1.0; }
+        }
+        shift = log(p);
+    }
+    const double ix = 1.0 / x, ix2 = ix * ix;
+    const double corr = ix * (1.0 / 12.0 + ix2 * (-1.0 / 360.0 + ix2 * (1.0 / 1260.0 +
+        ix2 * (-1.0 / 1680.0 + ix2 * (1.0 / 1188.0 + ix2 * (-691.0 / 360360.0 +
+        ix2 * (1.0 / 156.0)))))));
+    return ((x - 0.5) * log(x) - x + 0.9189385332046727 + corr) - shift;
 }
 
 // ---------------------------------------------------------------------------

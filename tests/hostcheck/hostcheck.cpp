@@ -29,6 +29,9 @@ void hc_q2q(const double* x, const double* mu_in, const double* mu_out, double a
             int n, double* out) {
     for (int i = 0; i < n; ++i) out[i] = h3d::q2q_one(x[i], mu_in[i], mu_out[i], alpha);
 }
+void hc_lgamma_pos(const double* x, int n, double* out) {
+    for (int i = 0; i < n; ++i) out[i] = h3d::lgamma_pos(x[i]);
+}
 void hc_chi2_sf(const double* x, int n, int df, double* out) {
     for (int i = 0; i < n; ++i) out[i] = h3d::chi2_sf(x[i], df);
 }
