@@ -119,7 +119,7 @@ equalize_kernel(const double* __restrict__ x, const double* __restrict__ f, long
                     const int r = cr.rep[c][k];
                     xr[k] = x[(long long)r * ld + i];
                     fr[k] = f[(long long)r * ld + i];
-                    slog += log(fr[k]);
+                    slog += m_log(fr[k]);
                 }
             }
             if (estimator == H3D_EST_CML) {
@@ -132,7 +132,7 @@ equalize_kernel(const double* __restrict__ x, const double* __restrict__ f, long
             // equalize (scaled_nb.py:207-214)
             double mu_hat = 1.0, mu_out = 1.0;
             if (valid) {
-                const double f_mean = exp(slog / (double)nr);       // gmean, pseudocount 0
+                const double f_mean = m_exp(slog / (double)nr);     // gmean, pseudocount 0
                 int st = 0;
                 mu_hat = fit_mu<MAXRC>(xr, fr, ar, (1u << nr) - 1u, &st);
                 if (st) atomicAdd(&cnt->n_fit_failed, 1);
@@ -221,17 +221,39 @@ nll_kernel(const double* __restrict__ pseudo, long long ld, const int* __restric
     const long long hi = (lo + kChunk < seg_hi) ? lo + kChunk : seg_hi;
     const double* __restrict__ base = pseudo + (long long)cr.pseudo_row[c] * ld;
     double acc = 0.0;
-    for (long long i = lo + threadIdx.x; i < hi; i += 256) {
-        double z = 0.0, lg = 0.0;
+    if (r >= 10.0) {
+        // every argument y + r is >= 10: Stirling without the shift, and the
+        // "- x" terms of the (R_c + 1) log-gammas cancel exactly
+        // (sum_k (y_k + r) == z + n r), so the per-pixel term is
+        //   sum_k [(x_k - .5) ln x_k + c(x_k)] - [(X - .5) ln X + c(X)] + (n-1) .5 ln 2pi
+        const double cst2 = cst + (double)(nr - 1) * 0.9189385332046727;
+        for (long long i = lo + threadIdx.x; i < hi; i += 256) {
+            double z = 0.0, t = 0.0;
 #pragma unroll
-        for (int k = 0; k < MAXRC; ++k) {
-            if (k < nr) {
-                const double y = base[(long long)k * ld + i];
-                z += y;
-                lg += lgamma_pos(y + r);
+            for (int k = 0; k < MAXRC; ++k) {
+                if (k < nr) {
+                    const double y = base[(long long)k * ld + i];
+                    z += y;
+                    const double xk = y + r;
+                    t += (xk - 0.5) * m_log(xk) + stirling_corr(xk);
+                }
             }
+            const double X = z + nrr;
+            acc += (t + cst2) - ((X - 0.5) * m_log(X) + stirling_corr(X));
         }
-        acc += (lg + cst) - lgamma_pos(z + nrr);
+    } else {
+        for (long long i = lo + threadIdx.x; i < hi; i += 256) {
+            double z = 0.0, lg = 0.0;
+#pragma unroll
+            for (int k = 0; k < MAXRC; ++k) {
+                if (k < nr) {
+                    const double y = base[(long long)k * ld + i];
+                    z += y;
+                    lg += lgamma_pos(y + r);
+                }
+            }
+            acc += (lg + cst) - lgamma_pos(z + nrr);
+        }
     }
     const double tot = block_sum_256(acc, sh);
     if (threadIdx.x == 0) partial[(long long)c * n_chunks + blockIdx.x] = tot;

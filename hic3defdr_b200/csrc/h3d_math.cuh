@@ -37,6 +37,14 @@ namespace h3d {
 constexpr int kMaxReps = 16;
 constexpr double kEps = 2.220446049250313e-16;
 
+// One out-of-line copy per kernel of the library transcendentals that the
+// special-function code calls from many places: inlined, they made up 40 % of
+// equalize_kernel's 77 KB of SASS and the warps starved on instruction fetch
+// (ncu: stall "no instruction" dominant).
+H3D_HDN double m_log(double x) { return log(x); }
+H3D_HDN double m_exp(double x) { return exp(x); }
+H3D_HDN double m_log1p(double x) { return log1p(x); }
+
 // ---------------------------------------------------------------------------
 // fit_mu: the unique positive root of
 //     g(mu) = sum_r (x_r - mu b_r) / (mu + alpha_r mu^2 b_r)
@@ -120,21 +128,25 @@ H3D_HD double log1p_minus_x(double u) {
         for (int k = 27; k >= 3; k -= 2) s = s * w2 + 1.0 / (double)k;
         return 2.0 * w * w2 * s - u * w;
     }
-    return log1p(u) - u;
+    return m_log1p(u) - u;
 }
 
 struct GammaShape {
     double a;
     double lead;   // a >= 10: 0.5 ln(a / 2 pi) - stirling(a);  else: -lgamma(a)
     double inv_a;
+    double lg_a1;  // ln Gamma(a + 1)
     bool big;
 };
+
+H3D_HD double lgamma_pos(double x);
 
 H3D_HDN GammaShape gamma_shape(double a) {
     GammaShape s;
     s.a = a;
     s.inv_a = 1.0 / a;
     s.big = a >= 10.0;
+    const double la = m_log(a);
     if (s.big) {
         // direct a ln x - x - lgamma(a) cancels catastrophically for large a;
         // Stirling: ln Gamma(a) = (a - .5) ln a - a + .5 ln 2pi + corr(a)
@@ -142,9 +154,12 @@ H3D_HDN GammaShape gamma_shape(double a) {
         const double corr = ia * (1.0 / 12.0 + ia2 * (-1.0 / 360.0 + ia2 * (1.0 / 1260.0 +
             ia2 * (-1.0 / 1680.0 + ia2 * (1.0 / 1188.0 + ia2 * (-691.0 / 360360.0 +
             ia2 * (1.0 / 156.0)))))));
-        s.lead = 0.5 * log(a * 0.15915494309189535) - corr;
+        s.lead = 0.5 * (la - 1.8378770664093453) - corr;
+        s.lg_a1 = (a + 0.5) * la - a + 0.9189385332046727 + corr;
     } else {
-        s.lead = -lgamma(a);
+        const double lga = lgamma_pos(a);
+        s.lead = -lga;
+        s.lg_a1 = lga + la;
     }
     return s;
 }
@@ -155,10 +170,10 @@ H3D_HD double gamma_logk(const GammaShape& s, double x) {
         const double u = (x - s.a) * s.inv_a;
         // away from u = 0 take the log of x / a itself: log1p(u) would inherit
         // the rounding of u, amplified by 1 / (1 + u) in the far left tail
-        const double l = (fabs(u) < 0.25) ? log1p_minus_x(u) : log(x * s.inv_a) - u;
+        const double l = (fabs(u) < 0.25) ? log1p_minus_x(u) : m_log(x * s.inv_a) - u;
         return s.lead + s.a * l;
     }
-    return s.a * log(x) - x + s.lead;
+    return s.a * m_log(x) - x + s.lead;
 }
 
 // S(a, x) = (1/a) * sum_{n>=0} x^n / ((a+1)...(a+n)); terms decrease
@@ -210,29 +225,24 @@ H3D_HD bool gamma_use_series(double a, double x) {
     return (x < 1.0) || (x < a);
 }
 
-// log of the lower (upper = false) or upper tail at y > 0, and
-// ratio = T / (y * pdf(y)) (so that d log T / d log y = -/+ 1 / ratio).
+// log of the lower (upper = false) or upper tail at y > 0,
+// ratio = T / (y * pdf(y)) (so that d log T / d log y = -/+ 1 / ratio), and the
+// log of the kernel k(a, y).
 // (not inlined on purpose: one copy of the series / continued-fraction code per
 // kernel keeps the hot loop inside the instruction cache)
 H3D_HDN void gamma_log_tail(const GammaShape& s, double y, bool upper, double* log_t,
-                            double* ratio) {
+                            double* ratio, double* log_k) {
     H3D_STAT(n_tail_eval);
     const double lk = gamma_logk(s, y);
-    if (gamma_use_series(s.a, y)) {
-        const double S = gamma_series_factor(s.a, y);
-        const double lp = lk + log(S);
-        if (!upper) { *log_t = lp; *ratio = S; return; }
-        const double T = -expm1(lp);                 // 1 - P
-        *log_t = log1p(-exp(lp));
-        *ratio = T / exp(lk);
-    } else {
-        const double H = gamma_cf_factor(s.a, y);
-        const double lq = lk + log(H);
-        if (upper) { *log_t = lq; *ratio = H; return; }
-        const double T = -expm1(lq);                 // 1 - Q
-        *log_t = log1p(-exp(lq));
-        *ratio = T / exp(lk);
-    }
+    *log_k = lk;
+    const bool series = gamma_use_series(s.a, y);
+    const double F = series ? gamma_series_factor(s.a, y) : gamma_cf_factor(s.a, y);
+    const double l_direct = lk + m_log(F);          // log P (series) or log Q (fraction)
+    if (series != upper) { *log_t = l_direct; *ratio = F; return; }
+    // the complementary tail was asked for
+    const double c = m_exp(l_direct);
+    *log_t = m_log1p(-c);
+    *ratio = (1.0 - c) * m_exp(-lk);
 }
 
 H3D_HD double gamma_p(double a, double x, double lga) {
@@ -240,8 +250,8 @@ H3D_HD double gamma_p(double a, double x, double lga) {
     if (!(x > 0.0)) return (x == 0.0) ? 0.0 : NAN;
     if (isinf(x)) return 1.0;
     const GammaShape s = gamma_shape(a);
-    double lt, ratio;
-    gamma_log_tail(s, x, false, &lt, &ratio);
+    double lt, ratio, lk;
+    gamma_log_tail(s, x, false, &lt, &ratio, &lk);
     return exp(lt);
 }
 
@@ -250,8 +260,8 @@ H3D_HD double gamma_q(double a, double x, double lga) {
     if (!(x > 0.0)) return (x == 0.0) ? 1.0 : NAN;
     if (isinf(x)) return 0.0;
     const GammaShape s = gamma_shape(a);
-    double lt, ratio;
-    gamma_log_tail(s, x, true, &lt, &ratio);
+    double lt, ratio, lk;
+    gamma_log_tail(s, x, true, &lt, &ratio, &lk);
     return exp(lt);
 }
 
@@ -268,17 +278,14 @@ H3D_HD double gamma_log_tail_inv(const GammaShape& s, double lt, bool upper, dou
     double lo = 0.0, hi = INFINITY;
     double y = (guess > 0.0 && isfinite(guess)) ? guess : a;
     if (!upper) {
-        // far lower tail: P(a,y) ~ y^a / Gamma(a+1);  lead = -lgamma(a) for small a
-        const double lg_a1 = s.big ? ((a - 0.5) * log(a) - a + 0.9189385332046727 +
-                                      (0.5 * log(a * 0.15915494309189535) - s.lead)) + log(a)
-                                   : -s.lead + log(a);
-        const double ys = exp((lt + lg_a1) * s.inv_a);
+        // far lower tail: P(a,y) ~ y^a / Gamma(a+1)
+        const double ys = m_exp((lt + s.lg_a1) * s.inv_a);
         if (ys < 0.2 * (a + 1.0)) y = ys;
     }
     if (!(y > 0.0)) y = 1.0;
     for (int it = 0; it < 100; ++it) {
-        double lT, ratio;
-        gamma_log_tail(s, y, upper, &lT, &ratio);
+        double lT, ratio, lk;
+        gamma_log_tail(s, y, upper, &lT, &ratio, &lk);
         if (lT == lt) return y;
         // bracket update: upper tail decreases in y, lower tail increases
         const bool y_too_small = upper ? (lT > lt) : (lT < lt);
@@ -299,7 +306,7 @@ H3D_HD double gamma_log_tail_inv(const GammaShape& s, double lt, bool upper, dou
                 const double kap = 1.0 / ratio;
                 double den = 2.0 * kap - g * (a - y - kap);
                 if (!(den > kap)) den = 2.0 * kap;
-                nxt = y * exp(-2.0 * g / den);
+                nxt = y * m_exp(-2.0 * g / den);
             }
             // a step this small means nxt is converged to round-off (the next
             // correction would be below 1e-18 relative)
@@ -323,12 +330,13 @@ H3D_HD double gamma_tail_inv(double a, double t, double lga, bool upper, double 
     (void)lga;
     if (!(t > 0.0)) return (t == 0.0) ? (upper ? INFINITY : 0.0) : NAN;
     if (t >= 1.0) return (t == 1.0) ? (upper ? 0.0 : INFINITY) : NAN;
-    return gamma_log_tail_inv(gamma_shape(a), log(t), upper, guess);
+    return gamma_log_tail_inv(gamma_shape(a), m_log(t), upper, guess);
 }
 
 // Wilson-Hilferty: Gamma(a,1) variate as a cube of a normal one.
 H3D_HD double wh_to_normal(double a, double x) {
-    return (cbrt(x / a) - (1.0 - 1.0 / (9.0 * a))) * 3.0 * sqrt(a);
+    // cube root through the shared log / exp (only seeds an iteration)
+    return (m_exp(m_log(x / a) * (1.0 / 3.0)) - (1.0 - 1.0 / (9.0 * a))) * 3.0 * sqrt(a);
 }
 H3D_HD double wh_from_normal(double a, double z) {
     const double t = 1.0 - 1.0 / (9.0 * a) + z / (3.0 * sqrt(a));
@@ -379,11 +387,11 @@ H3D_HD double q2q_one(double x, double mu_in, double mu_out, double alpha) {
         q_gamma = 0.0;                       // cdf(0) = 0 -> ppf(0) = 0
     } else {
         const GammaShape s_in = gamma_shape(a_in);
-        double lt, ratio;
-        gamma_log_tail(s_in, xs, right, &lt, &ratio);
+        double lt, ratio, lk;
+        gamma_log_tail(s_in, xs, right, &lt, &ratio, &lk);
         // cephes igam/igamc flush to zero when the kernel x^a e^-x / Gamma(a)
-        // underflows exp(-MAXLOG); ratio > 0 keeps log(kernel) = lt - log(ratio)
-        if (lt - log(ratio) < -709.782712893384 || lt < -744.44) {
+        // underflows exp(-MAXLOG)
+        if (lk < -709.782712893384 || lt < -744.44) {
             q_gamma = right ? INFINITY : 0.0;            // sf / cdf underflow in the reference
         } else {
             double guess = xs * (a_out / a_in);
@@ -405,6 +413,19 @@ H3D_HD double q2q_one(double x, double mu_in, double mu_out, double alpha) {
 // Gamma(x) = Gamma(x + n) / (x (x+1) ... (x+n-1)) below.  One log (two below
 // 10) and one reciprocal instead of the general-purpose library routine.
 // ---------------------------------------------------------------------------
+// correction term of Stirling's series for x >= 10 (truncation < 2e-17)
+H3D_HD double stirling_corr(double x) {
+#ifdef __CUDA_ARCH__
+    const double ix = __drcp_rn(x);
+#else
+    const double ix = 1.0 / x;
+#endif
+    const double ix2 = ix * ix;
+    return ix * (1.0 / 12.0 + ix2 * (-1.0 / 360.0 + ix2 * (1.0 / 1260.0 +
+        ix2 * (-1.0 / 1680.0 + ix2 * (1.0 / 1188.0 + ix2 * (-691.0 / 360360.0 +
+        ix2 * (1.0 / 156.0)))))));
+}
+
 H3D_HD double lgamma_pos(double x) {
     double shift = 0.0;
     if (x < 10.0) {
@@ -413,13 +434,13 @@ H3D_HD double lgamma_pos(double x) {
         for (int k = 0; k < 10; ++k) {
             if (x < 10.0) { p *= x; x += 1.0; }
         }
-        shift = log(p);
+        shift = m_log(p);
     }
     const double ix = 1.0 / x, ix2 = ix * ix;
     const double corr = ix * (1.0 / 12.0 + ix2 * (-1.0 / 360.0 + ix2 * (1.0 / 1260.0 +
         ix2 * (-1.0 / 1680.0 + ix2 * (1.0 / 1188.0 + ix2 * (-691.0 / 360360.0 +
         ix2 * (1.0 / 156.0)))))));
-    return ((x - 0.5) * log(x) - x + 0.9189385332046727 + corr) - shift;
+    return ((x - 0.5) * m_log(x) - x + 0.9189385332046727 + corr) - shift;
 }
 
 // ---------------------------------------------------------------------------
