@@ -338,8 +338,13 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     lib().query('h3d_reset_launch_count')
+    from hic3defdr_b200 import trace
+    trace.reset()
     ms, out = timed(step_device, args.steps)
     launches = int(lib().query('h3d_launch_count'))
+    if rank == 0:
+        trace.report('step_device, rank 0, per step', args.steps)
+    trace.reset()
     stats = out[3]
     del out
     # ---- e2e: host buffers in, host buffers out --------------------------
@@ -347,6 +352,8 @@ def main():
     ms_e2e, out_e2e = timed(step_e2e, args.steps)
     d2h = out_e2e[2]
     del out_e2e
+    if rank == 0:
+        trace.report('step_e2e, rank 0, per step', args.steps)
     sampler.stop_flag = True
     sampler.join()
     h2d = sum(h.nbytes for h, _ in host_inputs)

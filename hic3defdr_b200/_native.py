@@ -52,6 +52,8 @@ SIGNATURES = {
                               c_int, c_int, c_int, vp, vp, vp, vp, vp, vp]),
     'h3d_bh': (c_int, [vp, c_ll, vp, vp, c_sz, vp]),
     'h3d_bh_ws_bytes': (c_sz, [c_ll]),
+    'h3d_bh_ranked': (c_int, [vp, c_ll, c_ll, c_ll, vp, vp, vp, c_sz, vp]),
+    'h3d_bh_apply_carry': (c_int, [vp, c_ll, c_dbl, vp]),
 }
 
 

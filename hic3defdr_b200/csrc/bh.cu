@@ -57,22 +57,31 @@ __device__ __forceinline__ double key_to_double(unsigned long long b) {
     return __longlong_as_double((long long)b);
 }
 
-// raw BH ratio of the i-th smallest finite p-value: p / ((i + 1) / n)
+// raw BH ratio of the p-value of (1-based) rank i + 1 among n: p / ((i + 1) / n)
 __device__ __forceinline__ double bh_raw(unsigned long long key, long long i, double n) {
     return key_to_double(key) / ((double)(i + 1) / n);
 }
 
+// rank of the first local value minus one, and the number of tested hypotheses:
+// the local finite count for a single-device correction, host-supplied values
+// for one bucket of a distributed one
+struct BhScope { long long rank_offset, n_total; };
+__device__ __forceinline__ double bh_total(const BhScope& sc, long long nf) {
+    return (double)(sc.n_total > 0 ? sc.n_total : nf);
+}
+
 __global__ void __launch_bounds__(256)
 bh_tile_min_kernel(const unsigned long long* __restrict__ keys, const unsigned long long* __restrict__ n_finite,
-                   double* __restrict__ tile_min) {
+                   BhScope sc, double* __restrict__ tile_min) {
     __shared__ double sh[8];
     const long long nf = (long long)*n_finite;
     const long long base = (long long)blockIdx.x * kBhTile;
     if (base >= nf) return;
+    const double nt = bh_total(sc, nf);
     double m = INFINITY;
     for (int k = threadIdx.x; k < kBhTile; k += 256) {
         const long long i = base + k;
-        if (i < nf) m = fmin(m, bh_raw(keys[i], i, (double)nf));
+        if (i < nf) m = fmin(m, bh_raw(keys[i], sc.rank_offset + i, nt));
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_down_sync(0xffffffffu, m, o));
@@ -84,24 +93,46 @@ bh_tile_min_kernel(const unsigned long long* __restrict__ keys, const unsigned l
     }
 }
 
-// suffix minimum over tiles, exclusive: carry[t] = min over tiles > t
-__global__ void bh_tile_scan_kernel(const double* __restrict__ tile_min, const unsigned long long* __restrict__ n_finite,
-                                    double* __restrict__ carry) {
+// suffix minimum over tiles, exclusive: carry[t] = min over tiles > t; one
+// block, every thread owns a contiguous run of tiles.  Also reports the minimum
+// over all tiles (the bucket minimum of a distributed correction).
+__global__ void __launch_bounds__(1024)
+bh_tile_scan_kernel(const double* __restrict__ tile_min, const unsigned long long* __restrict__ n_finite,
+                    double* __restrict__ carry, double* __restrict__ min_out) {
+    __shared__ double sh[1024];
     const long long nf = (long long)*n_finite;
     const long long tiles = (nf + kBhTile - 1) / kBhTile;
+    const long long per = (tiles + 1023) / 1024;
+    const long long t0 = (long long)threadIdx.x * per;
+    const long long t1 = (t0 + per < tiles) ? t0 + per : tiles;
     double m = INFINITY;
-    for (long long t = tiles - 1; t >= 0; --t) {
-        carry[t] = m;
-        m = fmin(m, tile_min[t]);
+    for (long long t = t0; t < t1; ++t) m = fmin(m, tile_min[t]);
+    sh[threadIdx.x] = m;
+    __syncthreads();
+    // exclusive suffix min over threads (Hillis-Steele on the reversed order)
+    double incl = m;
+    for (int o = 1; o < 1024; o <<= 1) {
+        const double other = (threadIdx.x + o < 1024) ? sh[threadIdx.x + o] : INFINITY;
+        __syncthreads();
+        incl = fmin(incl, other);
+        sh[threadIdx.x] = incl;
+        __syncthreads();
+    }
+    double after = (threadIdx.x + 1 < 1024) ? sh[threadIdx.x + 1] : INFINITY;
+    if (threadIdx.x == 0 && min_out) *min_out = sh[0];
+    for (long long t = t1 - 1; t >= t0; --t) {
+        carry[t] = after;
+        after = fmin(after, tile_min[t]);
     }
 }
 
 __global__ void __launch_bounds__(256)
 bh_finish_kernel(const unsigned long long* __restrict__ keys, const int* __restrict__ idx,
                  const unsigned long long* __restrict__ n_finite, const double* __restrict__ carry,
-                 long long n, double* __restrict__ q) {
+                 BhScope sc, long long n, double* __restrict__ q) {
     __shared__ double sh[256];
     const long long nf = (long long)*n_finite;
+    const double nt = bh_total(sc, nf);
     const long long base = (long long)blockIdx.x * kBhTile;
     constexpr int per = kBhTile / 256;
     const long long first = base + (long long)threadIdx.x * per;
@@ -117,7 +148,7 @@ bh_finish_kernel(const unsigned long long* __restrict__ keys, const int* __restr
     double m = INFINITY;
     for (int k = per - 1; k >= 0; --k) {
         const long long i = first + k;
-        if (i < nf) m = fmin(m, bh_raw(keys[i], i, (double)nf));
+        if (i < nf) m = fmin(m, bh_raw(keys[i], sc.rank_offset + i, nt));
         v[k] = m;                      // suffix min inside the thread's run
     }
     sh[threadIdx.x] = m;
@@ -137,6 +168,17 @@ bh_finish_kernel(const unsigned long long* __restrict__ keys, const int* __restr
     }
 }
 
+// q <- min(q, carry), NaN kept (a distributed correction's contribution of
+// the buckets holding larger p-values)
+__global__ void __launch_bounds__(256)
+bh_apply_carry_kernel(double* __restrict__ q, long long n, double carry) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const double v = q[i];
+        if (v > carry) q[i] = carry;
+    }
+}
+
 }  // namespace h3d
 
 using namespace h3d;
@@ -152,9 +194,31 @@ extern "C" size_t h3d_bh_ws_bytes(long long n) {
 
 extern "C" int h3d_bh(const double* p, long long n, double* q, void* ws, size_t ws_bytes,
                       h3d_stream_t stream) {
-    if (n <= 0) return H3D_OK;
-    H3D_REQUIRE(n < 2147483647LL, "more than 2^31 p-values");
+    return h3d_bh_ranked(p, n, 0, 0, q, nullptr, ws, ws_bytes, stream);
+}
+
+extern "C" int h3d_bh_apply_carry(double* q, long long n, double carry, h3d_stream_t stream) {
+    if (n <= 0 || !(carry < 1.0)) return H3D_OK;      // q is already clipped at 1
+    bh_apply_carry_kernel<<<div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(q, n, carry);
+    H3D_LAUNCHED("bh_apply_carry_kernel");
+    return H3D_OK;
+}
+
+extern "C" int h3d_bh_ranked(const double* p, long long n, long long rank_offset, long long n_total,
+                             double* q, double* min_out, void* ws, size_t ws_bytes,
+                             h3d_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
+    if (n <= 0) {
+        if (min_out) {
+            const double inf = INFINITY;
+            H3D_CHECK(cudaMemcpyAsync(min_out, &inf, 8, cudaMemcpyHostToDevice, st));
+            H3D_CHECK(cudaStreamSynchronize(st));
+        }
+        return H3D_OK;
+    }
+    H3D_REQUIRE(n < 2147483647LL, "more than 2^31 p-values");
+    H3D_REQUIRE(rank_offset >= 0 && n_total >= 0, "negative rank offset / total");
+    const BhScope sc = {rank_offset, n_total};
     Workspace w(ws, ws_bytes);
     const long long tiles = (n + kBhTile - 1) / kBhTile;
     unsigned long long* keys_a = w.take<unsigned long long>(n);
@@ -191,11 +255,11 @@ extern "C" int h3d_bh(const double* p, long long n, double* q, void* ws, size_t 
         int* ti = idx_a; idx_a = idx_b; idx_b = ti;
         shift += bits;
     }
-    bh_tile_min_kernel<<<(int)tiles, 256, 0, st>>>(keys_a, n_finite, tile_min);
+    bh_tile_min_kernel<<<(int)tiles, 256, 0, st>>>(keys_a, n_finite, sc, tile_min);
     H3D_LAUNCHED("bh_tile_min_kernel");
-    bh_tile_scan_kernel<<<1, 1, 0, st>>>(tile_min, n_finite, carry);
+    bh_tile_scan_kernel<<<1, 1024, 0, st>>>(tile_min, n_finite, carry, min_out);
     H3D_LAUNCHED("bh_tile_scan_kernel");
-    bh_finish_kernel<<<(int)tiles, 256, 0, st>>>(keys_a, idx_a, n_finite, carry, n, q);
+    bh_finish_kernel<<<(int)tiles, 256, 0, st>>>(keys_a, idx_a, n_finite, carry, sc, n, q);
     H3D_LAUNCHED("bh_finish_kernel");
     return H3D_OK;
 }

@@ -83,17 +83,24 @@ def _all_gather_counts(local_counts):
     return np.stack([o.cpu().numpy() for o in out])
 
 
-def _regroup_order(keys):
-    """positions that sort ``keys`` stably (receiver-side regrouping)."""
-    if keys.is_cuda:
-        from hic3defdr_b200 import ops
-        n_keys = int(keys.max().item()) + 1 if keys.numel() else 1
-        r, _ = ops.stable_rank(keys, n_keys)
-        return r.long()
-    order = torch.argsort(keys, stable=True)
-    r = torch.empty_like(order)
-    r[order] = torch.arange(len(order))
-    return r
+def regroup_positions(recv_counts, device):
+    """Received layout is [source rank][owned distance] (runs of
+    ``recv_counts[s, d]`` pixels); wanted is [owned distance][source rank].
+    Returns the int64 destination of every received element: run (s, d) starts
+    at R[s, d] on arrival and at T[d, s] in the regrouped array, so
+    ``pos = arange + repeat(T - R)`` -- no sort, no host-side expansion."""
+    c = np.asarray(recv_counts, dtype=np.int64)               # (ws, owned)
+    n = int(c.sum())
+    flat = c.ravel()                                          # arrival order
+    r_start = np.concatenate([[0], np.cumsum(flat)[:-1]])
+    t_start = np.concatenate([[0], np.cumsum(c.T.ravel())[:-1]]) \
+        .reshape(c.shape[1], c.shape[0]).T.ravel()            # T[d, s] at (s, d)
+    shift = torch.from_numpy(t_start - r_start).to(device)
+    reps = torch.from_numpy(flat).to(device)
+    pos = torch.arange(n, dtype=torch.int64, device=device)
+    if n:
+        pos += torch.repeat_interleave(shift, reps, output_size=n)
+    return pos
 
 
 def exchange_by_distance(x, f, seg_start, n_local):
@@ -118,16 +125,16 @@ def exchange_by_distance(x, f, seg_start, n_local):
     n_recv = int(sum(recv_splits))
     xr = torch.empty((n_reps, max(n_recv, 1)), dtype=x.dtype, device=x.device)
     fr = torch.empty_like(xr)
+    works = []
     for r in range(n_reps):
         for src, dst in ((x, xr), (f, fr)):
-            td.all_to_all_single(dst[r, :n_recv], src[r, :n_local].contiguous(),
-                                 output_split_sizes=recv_splits,
-                                 input_split_sizes=send_splits)
-    # received layout: [source rank][distance]; wanted: [distance][source rank]
-    keys = torch.from_numpy(np.concatenate(
-        [np.repeat(np.arange(hi - lo), c) for c in recv_counts]
-        + [np.zeros(0, dtype=np.int64)]).astype(np.int32)).to(x.device)
-    pos = _regroup_order(keys)
+            works.append(td.all_to_all_single(
+                dst[r, :n_recv], src[r, :n_local],
+                output_split_sizes=recv_splits, input_split_sizes=send_splits,
+                async_op=True))
+    pos = regroup_positions(recv_counts, x.device)
+    for w in works:
+        w.wait()
     xo = torch.empty_like(xr)
     fo = torch.empty_like(fr)
     if n_recv:
@@ -171,14 +178,84 @@ def all_gather_varlen(local):
     return torch.cat([o[:int(s)] for o, s in zip(out, sizes)]), sizes
 
 
-def global_bh(local_p, bh_fn=None):
-    """BH over the p-values of all ranks; returns this rank's q-values."""
+BH_SAMPLES = 4096      # splitter candidates contributed by each rank
+
+
+def _partition(bucket, n_buckets):
+    """Stable partition by bucket id: (position of every element in
+    bucket-major order, bucket sizes as a host int64 array)."""
+    if bucket.is_cuda:
+        from hic3defdr_b200 import ops
+        pos, start = ops.stable_rank(bucket, n_buckets)
+        return pos.long(), np.diff(start.cpu().numpy())
+    order = torch.argsort(bucket, stable=True)
+    pos = torch.empty_like(order)
+    pos[order] = torch.arange(len(order))
+    return pos, np.bincount(bucket.numpy(), minlength=n_buckets).astype(np.int64)
+
+
+def global_bh(local_p, bh_fn=None, bh_ranked_fn=None, carry_fn=None):
+    """BH over the p-values of all ranks (hic3defdr/analysis/analysis.py:
+    296-303); returns this rank's q-values.
+
+    Multi-process: a distributed sort/rank.  Splitters from an all-gathered
+    sample cut [0, 1] into one value range per rank; ONE all-to-all moves every
+    p-value (8 B) to the owner of its range; the owner ranks its bucket locally
+    (global rank = local rank + sizes of the lower buckets), computes
+    p n / rank and the running minimum inside the bucket; the bucket minima
+    (one double per rank) are all-gathered for the carry across buckets; the
+    q-values return by the mirrored all-to-all.  Equal p-values always land in
+    the same bucket, so the result is identical to the single-process one."""
     if bh_fn is None:
         from hic3defdr_b200 import ops
-        bh_fn = ops.adjust_pvalues
-    if world_size() == 1:
+        bh_fn, bh_ranked_fn, carry_fn = ops.adjust_pvalues, \
+            ops.adjust_pvalues_ranked, ops.apply_bh_carry
+    ws, me = world_size(), rank()
+    if ws == 1:
         return bh_fn(local_p)
-    allp, sizes = all_gather_varlen(local_p)
-    q = bh_fn(allp)
-    start = int(sizes[:rank()].sum())
-    return q[start:start + int(sizes[rank()])]
+    n = local_p.numel()
+    device = local_p.device
+    finite = torch.isfinite(local_p)
+    # splitters: evenly strided local sample of the finite values
+    fin_vals = local_p[finite]
+    n_fin = fin_vals.numel()
+    sample = torch.full((BH_SAMPLES,), float('inf'), dtype=local_p.dtype,
+                        device=device)
+    if n_fin:
+        take = min(BH_SAMPLES, n_fin)
+        sel = torch.linspace(0, n_fin - 1, take, device=device).long()
+        sample[:take] = fin_vals[sel]
+    gathered = [torch.empty_like(sample) for _ in range(ws)]
+    td.all_gather(gathered, sample)
+    allsamp = torch.sort(torch.cat(gathered)).values
+    n_samp = int(torch.isfinite(allsamp).sum().item())
+    cut = [min(max(n_samp * k // ws, 0), max(n_samp - 1, 0))
+           for k in range(1, ws)]
+    splitters = allsamp[torch.tensor(cut, dtype=torch.long, device=device)]
+    # bucket of every local value (non-finite: last bucket), stable partition
+    bucket = torch.bucketize(local_p, splitters).to(torch.int32)
+    bucket = torch.where(finite, bucket, torch.full_like(bucket, ws - 1))
+    pos, sizes = _partition(bucket, ws)
+    send = torch.empty_like(local_p)
+    send[pos] = local_p
+    info = np.concatenate([sizes, [n_fin]])
+    table = _all_gather_counts(info)                 # (ws, ws + 1)
+    counts, n_total = table[:, :ws], int(table[:, ws].sum())
+    send_splits = [int(v) for v in counts[me]]
+    recv_splits = [int(v) for v in counts[:, me]]
+    recv = torch.empty(sum(recv_splits), dtype=local_p.dtype, device=device)
+    td.all_to_all_single(recv, send, output_split_sizes=recv_splits,
+                         input_split_sizes=send_splits)
+    # non-finite values sit in the last bucket only, so the sizes of the
+    # lower buckets are counts of finite values
+    rank_offset = int(counts[:, :me].sum())
+    q_bucket, bmin = bh_ranked_fn(recv, rank_offset, n_total)
+    mins = [torch.empty_like(bmin) for _ in range(ws)]
+    td.all_gather(mins, bmin)
+    higher = [float(m.item()) for m in mins[me + 1:]]
+    carry = min(higher) if higher else float('inf')
+    q_bucket = carry_fn(q_bucket, carry)
+    back = torch.empty_like(send)
+    td.all_to_all_single(back, q_bucket, output_split_sizes=send_splits,
+                         input_split_sizes=recv_splits)
+    return back[pos] if n else back

@@ -15,6 +15,7 @@ import torch
 
 from hic3defdr_b200 import dist as hdist
 from hic3defdr_b200 import ops
+from hic3defdr_b200.trace import stage
 from hic3defdr_b200.trend import lowess_fit, weighted_lowess_fit
 
 
@@ -121,18 +122,24 @@ def estimate_disp(states, design, dist_max, cond_names=None, estimator='qcml',
     n_conds = design.shape[1]
     if cond_names is None:
         cond_names = [str(c) for c in range(n_conds)]
-    x, f, dist_cat, seg_start, offs = pool_by_distance(states, dist_max)
+    with stage('estimate_disp/pool'):
+        x, f, dist_cat, seg_start, offs = pool_by_distance(states, dist_max)
     n_tot = int(offs[-1])
     # multi-GPU: every distance is estimated on the rank that owns it
-    x, f, seg_start, owner = hdist.exchange_by_distance(x, f, seg_start, n_tot)
-    disp_per_dist, stats = ops.estimate_dispersion(x, f, seg_start, design,
-                                                   estimator)
-    disp_per_dist = hdist.merge_disp_per_dist(disp_per_dist, owner)
+    with stage('estimate_disp/exchange'):
+        x, f, seg_start, owner = hdist.exchange_by_distance(x, f, seg_start,
+                                                            n_tot)
+    with stage('estimate_disp/qcml'):
+        disp_per_dist, stats = ops.estimate_dispersion(x, f, seg_start, design,
+                                                       estimator)
+    with stage('estimate_disp/merge'):
+        disp_per_dist = hdist.merge_disp_per_dist(disp_per_dist, owner)
     del x, f
-    fns, table = fit_trends(disp_per_dist, dist_max, cond_names, frac,
-                            auto_frac_factor, weighted_lowess, log)
-    disp = ops.gather_table(dist_cat, table) if n_tot else torch.empty(
-        (0, n_conds), dtype=torch.float64, device='cuda')
+    with stage('estimate_disp/trend'):
+        fns, table = fit_trends(disp_per_dist, dist_max, cond_names, frac,
+                                auto_frac_factor, weighted_lowess, log)
+        disp = ops.gather_table(dist_cat, table) if n_tot else torch.empty(
+            (0, n_conds), dtype=torch.float64, device='cuda')
     for i, s in enumerate(states):
         s['disp'] = disp[offs[i]:offs[i + 1]]
     return disp_per_dist, fns, stats
@@ -174,14 +181,18 @@ def run_to_qvalues(chrom_inputs, design, dist_min=4, dist_max=200,
     (ops.DeviceCSR, bias_raw CUDA tensor) for THIS rank's chromosomes.
     Returns (states, disp_per_dist, trend callables, qcml stats)."""
     design = np.asarray(design).astype(bool)
-    states = [prepare_chrom(csr, b, design, dist_min, dist_max, bias_thresh,
-                            mean_thresh, norm, n_bins)
-              for csr, b in chrom_inputs]
-    dpd, fns, stats = estimate_disp(states, design, dist_max,
-                                    estimator=estimator, frac=frac,
-                                    auto_frac_factor=auto_frac_factor,
-                                    weighted_lowess=weighted_lowess)
-    for s in states:
-        lrt_chrom(s, design, refit_mu)
-    bh(states)
+    with stage('prepare_data'):
+        states = [prepare_chrom(csr, b, design, dist_min, dist_max,
+                                bias_thresh, mean_thresh, norm, n_bins)
+                  for csr, b in chrom_inputs]
+    with stage('estimate_disp'):
+        dpd, fns, stats = estimate_disp(states, design, dist_max,
+                                        estimator=estimator, frac=frac,
+                                        auto_frac_factor=auto_frac_factor,
+                                        weighted_lowess=weighted_lowess)
+    with stage('lrt'):
+        for s in states:
+            lrt_chrom(s, design, refit_mu)
+    with stage('bh'):
+        bh(states)
     return states, dpd, fns, stats

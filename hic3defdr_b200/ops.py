@@ -431,3 +431,27 @@ def adjust_pvalues(pvalues):
     ws = workspace(wsb)
     lib().call('h3d_bh', ptr(p), n, ptr(q), ptr(ws), wsb, _stream())
     return q
+
+
+def adjust_pvalues_ranked(pvalues, rank_offset, n_total):
+    """One bucket of a multi-GPU BH correction (include/h3d.h,
+    h3d_bh_ranked): returns (q before the carry of the higher buckets, the
+    bucket's minimum raw ratio as a 1-element CUDA tensor)."""
+    p = dev(pvalues, torch.float64)
+    n = p.numel()
+    q = torch.empty_like(p)
+    mn = torch.full((1,), float('inf'), dtype=torch.float64, device='cuda')
+    if n == 0:
+        return q, mn
+    wsb = lib().query('h3d_bh_ws_bytes', n)
+    ws = workspace(wsb)
+    lib().call('h3d_bh_ranked', ptr(p), n, int(rank_offset), int(n_total),
+               ptr(q), ptr(mn), ptr(ws), wsb, _stream())
+    return q, mn
+
+
+def apply_bh_carry(q, carry):
+    """q <- min(q, carry) in place, NaN kept (h3d_bh_apply_carry)."""
+    lib().call('h3d_bh_apply_carry', ptr(q), q.numel(), float(carry),
+               _stream())
+    return q

@@ -1,0 +1,50 @@
+"""
+Stage tracing (off by default): ``H3D_TRACE=1`` makes every ``stage(name)``
+block synchronise the device on both sides and accumulate its wall time, so a
+run can print where a step's time goes (host glue, collectives and kernels
+together).  With tracing off the context manager costs one attribute lookup
+and never synchronises.  The reference prints progress per step to stderr
+(hic3defdr/util/printing.py:19); this is the timing-aware equivalent.
+"""
+import collections
+import contextlib
+import os
+import sys
+import time
+
+ENABLED = os.environ.get('H3D_TRACE', '0') not in ('', '0')
+TIMES = collections.OrderedDict()
+COUNTS = collections.Counter()
+
+
+@contextlib.contextmanager
+def stage(name):
+    if not ENABLED:
+        yield
+        return
+    import torch
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    try:
+        yield
+    finally:
+        torch.cuda.synchronize()
+        TIMES[name] = TIMES.get(name, 0.0) + time.perf_counter() - t0
+        COUNTS[name] += 1
+
+
+def reset():
+    TIMES.clear()
+    COUNTS.clear()
+
+
+def report(header='', divide_by=1, file=None):
+    if not ENABLED or not TIMES:
+        return
+    file = file or sys.stderr
+    tot = sum(v for k, v in TIMES.items() if '/' not in k)
+    print('[h3d trace] %s (top-level total %.1f ms)'
+          % (header, 1e3 * tot / divide_by), file=file)
+    for k, v in TIMES.items():
+        print('[h3d trace]   %-28s %9.2f ms  (%d calls)'
+              % (k, 1e3 * v / divide_by, COUNTS[k] // divide_by), file=file)

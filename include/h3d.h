@@ -221,6 +221,20 @@ int h3d_bh(const double* p, long long n, double* q, void* ws, size_t ws_bytes,
            h3d_stream_t stream);
 size_t h3d_bh_ws_bytes(long long n);
 
+/* One bucket of a multi-GPU correction (the distributed sort/rank of p-values
+ * that replaces the single argsort of statsmodels' fdr_bh): ``p`` holds every
+ * p-value of the genome that falls between two splitters, ``rank_offset`` of
+ * the genome's finite p-values are smaller, ``n_total`` are finite in total
+ * (0: the local finite count).  Writes q before the contribution of the
+ * buckets above (clipped at 1) and, to ``min_out`` (device, may be NULL), the
+ * smallest p / (rank / n_total) of the bucket; the caller exchanges the minima
+ * and finishes with h3d_bh_apply_carry(q, n, min over the higher buckets).
+ * Workspace as for h3d_bh. */
+int h3d_bh_ranked(const double* p, long long n, long long rank_offset, long long n_total,
+                  double* q, double* min_out, void* ws, size_t ws_bytes,
+                  h3d_stream_t stream);
+int h3d_bh_apply_carry(double* q, long long n, double carry, h3d_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

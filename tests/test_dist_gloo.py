@@ -76,14 +76,38 @@ def _worker(rank, world, port, ret):
         ok = counts > 0
         assert np.array_equal(merged[ok, 1], np.arange(n_dist)[ok] + 0.5)
         # 4. global BH equals BH over the concatenation
-        p_local = rng.random(300 + 17 * rank) ** 2
-        q_local = hd.global_bh(torch.from_numpy(p_local),
-                               bh_fn=lambda t: torch.from_numpy(op.bh(t.numpy())))
+        # (distributed sort/rank; ties across the splitter and NaN included)
+        p_local = rng.random(3000 + 170 * rank) ** 2
+        p_local[::7] = 0.25                 # heavy ties, the same on all ranks
+        p_local[5::31] = np.nan
+        p_local[3] = 1.0
+
+        def ranked(t, off, ntot):
+            p = t.numpy()
+            q = np.full(p.shape, np.nan)
+            fin = np.isfinite(p)
+            order = np.argsort(p[fin], kind='stable')
+            raw = p[fin][order] / ((off + np.arange(1, fin.sum() + 1))
+                                   / float(ntot))
+            sm = np.minimum.accumulate(raw[::-1])[::-1]
+            sm[sm > 1] = 1
+            out = np.empty(len(sm))
+            out[order] = sm
+            q[fin] = out
+            return torch.from_numpy(q), torch.tensor(
+                [raw.min() if len(raw) else np.inf])
+
+        q_local = hd.global_bh(
+            torch.from_numpy(p_local),
+            bh_fn=lambda t: torch.from_numpy(op.bh(t.numpy())),
+            bh_ranked_fn=ranked,
+            carry_fn=lambda q, c: torch.where(q > c, torch.full_like(q, c), q))
         allp = [None] * world
         td.all_gather_object(allp, p_local.tolist())
         q_all = op.bh(np.concatenate([np.array(v) for v in allp]))
         start = sum(len(v) for v in allp[:rank])
-        assert np.array_equal(q_local.numpy(), q_all[start:start + len(p_local)])
+        assert np.array_equal(q_local.numpy(), q_all[start:start + len(p_local)],
+                              equal_nan=True)
         ret[rank] = 'ok'
     except Exception as e:          # surface the failure in the parent
         import traceback
@@ -92,8 +116,8 @@ def _worker(rank, world, port, ret):
         td.destroy_process_group()
 
 
-def test_two_rank_host_logic():
-    world = 2
+@pytest.mark.parametrize('world', [2, 3])
+def test_multi_rank_host_logic(world):
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
