@@ -199,34 +199,45 @@ __device__ __forceinline__ double block_sum_256(double v, double* sh) {
     return t;
 }
 
-// conditional NB negative log-likelihood partials (dispersion.py:72-75)
+__global__ void logtab_init_kernel(LogTabEntry* __restrict__ tab) {
+    if (threadIdx.x < kLogTabSize) log_table_entry(threadIdx.x, &tab[threadIdx.x]);
+}
+
+// conditional NB negative log-likelihood partials (dispersion.py:72-75):
+//   sum_px [ sum_k lgamma(y_k + r) + lgamma(n r) - lgamma(z + n r) - n lgamma(r) ]
+// Every log-gamma goes through Stirling's series at an argument >= 10
+// (shifted up by the recurrence when smaller); the "- x" terms of the
+// (R_c + 1) log-gammas of a pixel cancel exactly (sum_k (y_k + r) == z + n r)
+// and are never computed, so the per-pixel term is
+//   sum_k [core(x_k) - n_k] - [core(X) - N] + (R_c - 1) .5 ln 2pi,
+// core(x) = (x - .5) ln x + corr(x) at the shifted argument minus the log of
+// the shift product, n = number of unit shifts.
 template <int MAXRC>
 __global__ void __launch_bounds__(256)
 nll_kernel(const double* __restrict__ pseudo, long long ld, const int* __restrict__ chunk_seg,
            const long long* __restrict__ chunk_lo, const long long* __restrict__ seg_start,
-           CondReps cr, const Problem* __restrict__ prob, double* __restrict__ partial,
-           int n_chunks) {
+           CondReps cr, const Problem* __restrict__ prob, const LogTabEntry* __restrict__ logtab,
+           double* __restrict__ partial, int n_chunks) {
     __shared__ double sh[8];
+    __shared__ LogTabEntry tab[kLogTabSize];
     const int c = blockIdx.y;
     const int s = chunk_seg[blockIdx.x];
     const Problem& q = prob[s * cr.n_conds + c];
     if (q.status != ST_IN_BRENT) return;
+    if (threadIdx.x < kLogTabSize) tab[threadIdx.x] = logtab[threadIdx.x];
+    __syncthreads();
     const double delta = q.brent.x_eval;
     const double r = 1.0 / delta - 1.0;
     const int nr = cr.n_in[c];
     const double nrr = (double)nr * r;
-    const double cst = lgamma_pos(nrr) - (double)nr * lgamma_pos(r);
+    const double cst = lgamma_pos(nrr) - (double)nr * lgamma_pos(r) +
+                       (double)(nr - 1) * 0.9189385332046727;
     const long long lo = chunk_lo[blockIdx.x];
     const long long seg_hi = seg_start[s + 1];
     const long long hi = (lo + kChunk < seg_hi) ? lo + kChunk : seg_hi;
     const double* __restrict__ base = pseudo + (long long)cr.pseudo_row[c] * ld;
     double acc = 0.0;
     if (r >= 10.0) {
-        // every argument y + r is >= 10: Stirling without the shift, and the
-        // "- x" terms of the (R_c + 1) log-gammas cancel exactly
-        // (sum_k (y_k + r) == z + n r), so the per-pixel term is
-        //   sum_k [(x_k - .5) ln x_k + c(x_k)] - [(X - .5) ln X + c(X)] + (n-1) .5 ln 2pi
-        const double cst2 = cst + (double)(nr - 1) * 0.9189385332046727;
         for (long long i = lo + threadIdx.x; i < hi; i += 256) {
             double z = 0.0, t = 0.0;
 #pragma unroll
@@ -234,25 +245,25 @@ nll_kernel(const double* __restrict__ pseudo, long long ld, const int* __restric
                 if (k < nr) {
                     const double y = base[(long long)k * ld + i];
                     z += y;
-                    const double xk = y + r;
-                    t += (xk - 0.5) * m_log(xk) + stirling_corr(xk);
+                    t += stirling_core(y + r, tab);
                 }
             }
-            const double X = z + nrr;
-            acc += (t + cst2) - ((X - 0.5) * m_log(X) + stirling_corr(X));
+            acc += (t + cst) - stirling_core(z + nrr, tab);
         }
     } else {
         for (long long i = lo + threadIdx.x; i < hi; i += 256) {
-            double z = 0.0, lg = 0.0;
+            double z = 0.0, t = 0.0, sh_n = 0.0, n1;
 #pragma unroll
             for (int k = 0; k < MAXRC; ++k) {
                 if (k < nr) {
                     const double y = base[(long long)k * ld + i];
                     z += y;
-                    lg += lgamma_pos(y + r);
+                    t += stirling_core_shifted(y + r, tab, &n1);
+                    sh_n += n1;
                 }
             }
-            acc += (lg + cst) - lgamma_pos(z + nrr);
+            const double tX = stirling_core_shifted(z + nrr, tab, &n1);
+            acc += ((t - tX) + cst) - (sh_n - n1);
         }
     }
     const double tot = block_sum_256(acc, sh);
@@ -395,6 +406,7 @@ extern "C" size_t h3d_estimate_dispersion_ws_bytes(long long n_px, int n_seg, in
     b += ws_pad((size_t)(n_seg + 1) * 8) + ws_pad((size_t)(n_seg + 1) * 4);
     b += ws_pad((size_t)n_seg * n_conds * sizeof(Problem));
     b += ws_pad((size_t)n_seg * n_conds * 8) + ws_pad(64) + ws_pad(64);
+    b += ws_pad((size_t)kLogTabSize * sizeof(LogTabEntry));
     return b;
 }
 
@@ -457,7 +469,8 @@ extern "C" int h3d_estimate_dispersion(const double* x, const double* f, long lo
     double* disp_dev = w.take<double>(n_prob);
     Counters* cnt = w.take<Counters>(1);
     long long* stats_dev = w.take<long long>(4);
-    if (!pseudo || !partial || !partial_cnt || !chunk_seg || !chunk_lo || !seg_start ||
+    LogTabEntry* logtab = w.take<LogTabEntry>(kLogTabSize);
+    if (!logtab || !partial || !partial_cnt || !chunk_seg || !chunk_lo || !seg_start ||
         !seg_chunk_start || !prob || !disp_dev || !cnt || !stats_dev) {
         set_error("estimate_dispersion workspace too small (%zu bytes given)", ws_bytes);
         return H3D_ERR_WORKSPACE;
@@ -469,6 +482,8 @@ extern "C" int h3d_estimate_dispersion(const double* x, const double* f, long lo
     // the host vectors must outlive the async copies
     H3D_CHECK(cudaStreamSynchronize(st));
 
+    logtab_init_kernel<<<1, kLogTabSize, 0, st>>>(logtab);
+    H3D_LAUNCHED("logtab_init_kernel");
     const int pgrid = div_up(n_prob, 128);
     init_problems_kernel<<<pgrid, 128, 0, st>>>(prob, seg_start, n_seg, n_conds, estimator, cnt);
     H3D_LAUNCHED("init_problems_kernel");
@@ -520,7 +535,7 @@ extern "C" int h3d_estimate_dispersion(const double* x, const double* f, long lo
             }
             H3D_CHECK(cudaEventRecord(ev[2], st));
 #define CALL(M) nll_kernel<M><<<cgrid, 256, 0, st>>>(pseudo, ld, chunk_seg, chunk_lo, seg_start, cr, prob, \
-        partial, n_chunks)
+        logtab, partial, n_chunks)
             DISPATCH_RC(CALL)
 #undef CALL
             H3D_LAUNCHED("nll_kernel");

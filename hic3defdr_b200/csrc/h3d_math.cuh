@@ -14,6 +14,7 @@
 #pragma once
 #include <math.h>
 #include <float.h>
+#include <string.h>
 
 #ifdef __CUDACC__
 #define H3D_HD __host__ __device__ __forceinline__
@@ -44,6 +45,63 @@ constexpr double kEps = 2.220446049250313e-16;
 H3D_HDN double m_log(double x) { return log(x); }
 H3D_HDN double m_exp(double x) { return exp(x); }
 H3D_HDN double m_log1p(double x) { return log1p(x); }
+
+// ---------------------------------------------------------------------------
+// Table-driven natural logarithm for positive, finite, normal arguments that
+// are not close to 1 (the log-gamma arguments y + r >= r of the conditional
+// likelihood, evaluated ~10^10 times per genome): x = 2^e m, m in [1, 2);
+// c_j ~ 1 / (centre of the j-th of 128 mantissa intervals);
+// ln x = e ln2 + (-ln c_j) + log1p(m c_j - 1), |m c_j - 1| <= 2^-8, so a
+// degree-7 polynomial suffices.  ~12 FP64 instructions instead of ~30 for the
+// general routine; error <= ~1.5 ulp for |ln x| >= 1 (the cancellation-free
+// range); checked against libm in tests/test_hostcheck_math.py.
+// ---------------------------------------------------------------------------
+struct LogTabEntry { double c, neg_log_c; };
+constexpr int kLogTabSize = 128;
+
+H3D_HD void log_table_entry(int j, LogTabEntry* e) {
+    const double c = 1.0 / (1.0 + ((double)j + 0.5) / (double)kLogTabSize);
+    e->c = c;
+    e->neg_log_c = -log(c);
+}
+
+H3D_HD double fast_log_pos(double x, const LogTabEntry* tab) {
+#ifdef __CUDA_ARCH__
+    const int hi = __double2hiint(x), lo = __double2loint(x);
+    const double m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, lo);
+#else
+    long long b;
+    memcpy(&b, &x, 8);
+    const int hi = (int)(b >> 32);
+    const long long mb = (b & 0x000FFFFFFFFFFFFFLL) | 0x3FF0000000000000LL;
+    double m;
+    memcpy(&m, &mb, 8);
+#endif
+    const int ex = (hi >> 20) - 1023;
+    const LogTabEntry t = tab[(hi >> 13) & (kLogTabSize - 1)];
+    const double r = fma(m, t.c, -1.0);
+    const double e = (double)ex;
+    double p = fma(r, 1.0 / 7.0, -1.0 / 6.0);
+    p = fma(p, r, 1.0 / 5.0);
+    p = fma(p, r, -1.0 / 4.0);
+    p = fma(p, r, 1.0 / 3.0);
+    p = fma(p, r, -0.5);
+    const double tail = fma(r * r, p, e * 2.319046813846299616e-17);      // + e ln2_lo
+    return fma(e, 0.693147180559945286, t.neg_log_c) + (r + tail);
+}
+
+// reciprocal of a positive normal number to ~1 ulp (not correctly rounded):
+// hardware seed (2^-23) refined by one cubic step
+H3D_HD double fast_rcp_pos(double x) {
+#ifdef __CUDA_ARCH__
+    double y0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+    const double e = fma(-x, y0, 1.0);
+    return fma(y0, fma(e, e, e), y0);
+#else
+    return 1.0 / x;
+#endif
+}
 
 // ---------------------------------------------------------------------------
 // fit_mu: the unique positive root of
@@ -424,6 +482,33 @@ H3D_HD double stirling_corr(double x) {
     return ix * (1.0 / 12.0 + ix2 * (-1.0 / 360.0 + ix2 * (1.0 / 1260.0 +
         ix2 * (-1.0 / 1680.0 + ix2 * (1.0 / 1188.0 + ix2 * (-691.0 / 360360.0 +
         ix2 * (1.0 / 156.0)))))));
+}
+
+// Stirling's series term of one log-gamma argument x >= 10 without the
+// "- x + .5 ln 2pi" part (which cancels or is constant in the conditional
+// likelihood): (x - .5) ln x + corr(x), table-driven log, refined-seed reciprocal
+H3D_HD double stirling_core(double x, const LogTabEntry* tab) {
+    const double ix = fast_rcp_pos(x);
+    const double ix2 = ix * ix;
+    const double corr = ix * (1.0 / 12.0 + ix2 * (-1.0 / 360.0 + ix2 * (1.0 / 1260.0 +
+        ix2 * (-1.0 / 1680.0 + ix2 * (1.0 / 1188.0 + ix2 * (-691.0 / 360360.0 +
+        ix2 * (1.0 / 156.0)))))));
+    return fma(x - 0.5, fast_log_pos(x, tab), corr);
+}
+
+// the same for any x > 0: arguments below 10 are shifted up by the recurrence,
+// log Gamma(x) = log Gamma(x + n) - ln(x (x+1) ... (x+n-1)); returns the core
+// of the shifted argument minus the log of the product and reports the shift n
+// (the caller accounts for the "- x" term: core(x + n) - (x + n) + ...)
+H3D_HD double stirling_core_shifted(double x, const LogTabEntry* tab, double* shifted_by) {
+    double p = 1.0, n = 0.0;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+        if (x < 10.0) { p *= x; x += 1.0; n += 1.0; }
+    }
+    *shifted_by = n;
+    // p >= 1 is not guaranteed (x < 1), and ln p may be near 0: general log
+    return stirling_core(x, tab) - ((n > 0.0) ? log(p) : 0.0);
 }
 
 H3D_HD double lgamma_pos(double x) {

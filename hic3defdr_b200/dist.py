@@ -7,12 +7,15 @@ How the path shards:
     ranks by longest-processing-time on the input size;
   * estimate_disp: dispersion is pooled genome-wide per distance
     (hic3defdr/analysis/analysis.py:169-206) -> ONE all-to-all moves every
-    rank's pixels of distance d to the rank owning d (contiguous distance
-    ranges balanced by pixel count); the (distance, condition) optimisations
-    then run without any collective, and the (D+1, C) result is all-gathered;
-  * bh: one global correction (analysis.py:296-303) -> p-values are
-    all-gathered (8 B per tested pixel over NVLink), every rank ranks the full
-    set and keeps the q-values of its own pixels.
+    rank's pixels of distance d to the rank owning d (distances dealt round
+    robin: balances pixel counts and qCML iterations); the (distance,
+    condition) optimisations then run without any collective, and the (D+1, C)
+    result is all-gathered;
+  * bh: one global correction (analysis.py:296-303) -> distributed sort/rank:
+    splitters from a gathered sample, one all-to-all of the p-values (8 B per
+    tested pixel over NVLink) to the owner of their value range, local ranking
+    with global rank offsets, all-gather of one carry per rank, q-values back
+    by the mirrored all-to-all.
 Single-process runs take none of these branches.
 """
 import numpy as np
@@ -59,21 +62,6 @@ def shard_chroms(chroms, weight_fn):
     return [c for c, o in zip(chroms, owner) if o == rank()]
 
 
-def distance_ranges(global_counts, n_ranks):
-    """Contiguous distance ranges [lo_k, hi_k) with balanced pixel counts.
-    Returns an int64 array of n_ranks + 1 boundaries."""
-    total = int(global_counts.sum())
-    cum = np.concatenate([[0], np.cumsum(global_counts)])
-    bounds = [0]
-    for k in range(1, n_ranks):
-        target = total * k / float(n_ranks)
-        b = int(np.searchsorted(cum, target, side='left'))
-        b = min(max(b, bounds[-1]), len(global_counts))
-        bounds.append(b)
-    bounds.append(len(global_counts))
-    return np.array(bounds, dtype=np.int64)
-
-
 def _all_gather_counts(local_counts):
     t = torch.from_numpy(np.ascontiguousarray(local_counts, dtype=np.int64))
     if td.get_backend() == 'nccl':
@@ -103,24 +91,42 @@ def regroup_positions(recv_counts, device):
     return pos
 
 
+def distance_keys(n_dist, n_ranks=None):
+    """Pooling key of every distance: distances are dealt to ranks round robin
+    (owner(d) = d mod n_ranks -- the cost of a (distance, condition) bin varies
+    smoothly with d, so interleaving balances pixels AND qCML iterations), and
+    the key orders a rank's pooled pixels by (owner, distance):
+    key(d) = owner(d) * per + d // n_ranks, per = ceil(n_dist / n_ranks).
+    Returns (key per distance int32, per).  Identity for one process."""
+    ws = world_size() if n_ranks is None else n_ranks
+    per = -(-n_dist // ws)
+    d = np.arange(n_dist)
+    return ((d % ws) * per + d // ws).astype(np.int32), per
+
+
+def owned_distances(n_dist, me=None, n_ranks=None):
+    """distances owned by rank ``me``, in key order"""
+    ws = world_size() if n_ranks is None else n_ranks
+    me = rank() if me is None else me
+    return np.arange(me, n_dist, ws)
+
+
 def exchange_by_distance(x, f, seg_start, n_local):
-    """x, f: (R, ld) pooled by distance on this rank; seg_start: (D + 2) local
-    group boundaries.  Returns (x, f, seg_start, owner) where the arrays hold
-    ALL ranks' pixels of the distances this rank owns (other distances are
-    empty segments) and ``owner`` is the boundary array (None when single
-    process)."""
-    if world_size() == 1:
-        return x, f, seg_start, None
+    """x, f: (R, ld) pooled on this rank in ``distance_keys`` order;
+    seg_start: (ws * per + 1) local group boundaries over the keys.  Returns
+    (x, f, seg_start) holding ALL ranks' pixels of the distances this rank
+    owns, one segment per owned key (``per`` segments, the trailing ones empty
+    when the distances do not divide evenly)."""
     ws, me = world_size(), rank()
-    n_dist = len(seg_start) - 1
+    if ws == 1:
+        return x, f, seg_start
+    per = (len(seg_start) - 1) // ws
     local_counts = np.diff(seg_start)
-    all_counts = _all_gather_counts(local_counts)          # (ws, n_dist)
-    bounds = distance_ranges(all_counts.sum(axis=0), ws)
+    all_counts = _all_gather_counts(local_counts)          # (ws, ws * per)
     n_reps = x.shape[0]
-    send_splits = [int(seg_start[bounds[k + 1]] - seg_start[bounds[k]])
+    send_splits = [int(seg_start[(k + 1) * per] - seg_start[k * per])
                    for k in range(ws)]
-    lo, hi = int(bounds[me]), int(bounds[me + 1])
-    recv_counts = all_counts[:, lo:hi]                      # (ws, owned)
+    recv_counts = all_counts[:, me * per:(me + 1) * per]    # (ws, per)
     recv_splits = [int(c.sum()) for c in recv_counts]
     n_recv = int(sum(recv_splits))
     xr = torch.empty((n_reps, max(n_recv, 1)), dtype=x.dtype, device=x.device)
@@ -140,30 +146,28 @@ def exchange_by_distance(x, f, seg_start, n_local):
     if n_recv:
         xo[:, pos] = xr[:, :n_recv]
         fo[:, pos] = fr[:, :n_recv]
-    owned = recv_counts.sum(axis=0)
-    seg = np.zeros(n_dist + 1, dtype=np.int64)
-    seg[lo + 1:hi + 1] = np.cumsum(owned)
-    seg[hi + 1:] = seg[hi]
-    return xo, fo, seg, bounds
+    seg = np.concatenate([[0], np.cumsum(recv_counts.sum(axis=0))]) \
+        .astype(np.int64)
+    return xo, fo, seg
 
 
-def merge_disp_per_dist(disp_local, bounds):
-    """Every rank contributes the rows of the distances it owns."""
-    if bounds is None:
-        return disp_local
-    t = torch.from_numpy(np.nan_to_num(disp_local, nan=0.0))
-    mask = torch.from_numpy(np.isfinite(disp_local).astype(np.float64))
-    lo, hi = int(bounds[rank()]), int(bounds[rank() + 1])
-    keep = torch.zeros_like(t)
-    keep[lo:hi] = 1
-    t, mask = t * keep, mask * keep
+def merge_disp_per_dist(disp_owned, n_dist):
+    """``disp_owned``: (per, C) results of this rank's owned distances (key
+    order).  Returns the full (n_dist, C) table on every rank."""
+    ws = world_size()
+    if ws == 1:
+        return disp_owned[:n_dist]
+    per, n_conds = disp_owned.shape
+    t = torch.from_numpy(np.ascontiguousarray(disp_owned))
     if td.get_backend() == 'nccl':
-        t, mask = t.cuda(), mask.cuda()
-    td.all_reduce(t)
-    td.all_reduce(mask)
-    out = t.cpu().numpy()
-    out[mask.cpu().numpy() == 0] = np.nan
-    return out
+        t = t.cuda()
+    out = [torch.empty_like(t) for _ in range(ws)]
+    td.all_gather(out, t)
+    full = np.full((n_dist, n_conds), np.nan)
+    for k in range(ws):
+        d = owned_distances(n_dist, k, ws)
+        full[d] = out[k].cpu().numpy()[:len(d)]
+    return full
 
 
 def all_gather_varlen(local):

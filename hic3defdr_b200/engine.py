@@ -53,9 +53,11 @@ def prepare_chrom(csr, bias_raw, design, dist_min=4, dist_max=200,
 def pool_by_distance(states, dist_max):
     """Pools the disp_idx pixels of the given chromosomes by distance
     (analysis/analysis.py:169-183, 196-197): returns (x, f) SoA (R, n) in
-    (distance, chromosome, row, col) order, the per-pixel distances in
-    chromosome order, the segment boundaries (host int64) and the
-    per-chromosome offsets."""
+    (distance key, chromosome, row, col) order, the per-pixel distances in
+    chromosome order, the segment boundaries over the keys (host int64) and
+    the per-chromosome offsets.  The key is the distance itself in a
+    one-process run and (owner rank, distance) otherwise
+    (hic3defdr_b200.dist.distance_keys)."""
     counts = [int(s['disp_index'].numel()) for s in states]
     offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
     n_tot = int(offs[-1])
@@ -73,8 +75,12 @@ def pool_by_distance(states, dist_max):
     x = torch.empty((n_reps, max(n_tot, 1)), dtype=torch.float64,
                     device='cuda')
     f = torch.empty_like(x)
+    key_of_dist, per = hdist.distance_keys(dist_max + 1)
+    n_keys = per * hdist.world_size()
     if n_tot:
-        rank, key_start = ops.stable_rank(dist_cat, dist_max + 1)
+        keys = dist_cat if hdist.world_size() == 1 else \
+            ops.dev(key_of_dist)[dist_cat.long()]
+        rank, key_start = ops.stable_rank(keys, n_keys)
         for s, o, n in zip(states, offs[:-1], counts):
             if n:
                 ops.gather_counts_factors(
@@ -83,7 +89,7 @@ def pool_by_distance(states, dist_max):
                     x, f, None)
         seg_start = key_start.cpu().numpy()
     else:
-        seg_start = np.zeros(dist_max + 2, dtype=np.int64)
+        seg_start = np.zeros(n_keys + 1, dtype=np.int64)
     return x, f, dist_cat, seg_start, offs
 
 
@@ -127,13 +133,12 @@ def estimate_disp(states, design, dist_max, cond_names=None, estimator='qcml',
     n_tot = int(offs[-1])
     # multi-GPU: every distance is estimated on the rank that owns it
     with stage('estimate_disp/exchange'):
-        x, f, seg_start, owner = hdist.exchange_by_distance(x, f, seg_start,
-                                                            n_tot)
+        x, f, seg_start = hdist.exchange_by_distance(x, f, seg_start, n_tot)
     with stage('estimate_disp/qcml'):
         disp_per_dist, stats = ops.estimate_dispersion(x, f, seg_start, design,
                                                        estimator)
     with stage('estimate_disp/merge'):
-        disp_per_dist = hdist.merge_disp_per_dist(disp_per_dist, owner)
+        disp_per_dist = hdist.merge_disp_per_dist(disp_per_dist, dist_max + 1)
     del x, f
     with stage('estimate_disp/trend'):
         fns, table = fit_trends(disp_per_dist, dist_max, cond_names, frac,
@@ -173,26 +178,46 @@ def bh(states, use_loop_idx=False):
     return states
 
 
+PREPARE_OUTPUTS = ('row', 'col', 'raw', 'size_factors', 'scaled', 'disp_idx')
+LRT_OUTPUTS = ('pvalues', 'llr', 'mu_hat_null', 'mu_hat_alt')
+
+
 def run_to_qvalues(chrom_inputs, design, dist_min=4, dist_max=200,
                    bias_thresh=0.1, mean_thresh=1.0, norm='conditional_mor',
                    n_bins=-1, estimator='qcml', frac=None,
-                   auto_frac_factor=15., weighted_lowess=True, refit_mu=True):
-    """All four steps on device inputs: ``chrom_inputs`` is a list of
-    (ops.DeviceCSR, bias_raw CUDA tensor) for THIS rank's chromosomes.
+                   auto_frac_factor=15., weighted_lowess=True, refit_mu=True,
+                   sink=None):
+    """All four steps on device inputs: ``chrom_inputs`` is an iterable of
+    (ops.DeviceCSR, bias_raw CUDA tensor) for THIS rank's chromosomes (a list,
+    or a ``staging.InputPrefetcher`` that uploads ahead of the kernels).
+    ``sink(i, name, tensor)``, if given, is called for every output array of
+    chromosome i as soon as it is final (``staging.OutputDrain`` starts its
+    device -> host copy there).
     Returns (states, disp_per_dist, trend callables, qcml stats)."""
     design = np.asarray(design).astype(bool)
+    emit = sink if sink is not None else (lambda i, name, t: None)
+    states = []
     with stage('prepare_data'):
-        states = [prepare_chrom(csr, b, design, dist_min, dist_max,
-                                bias_thresh, mean_thresh, norm, n_bins)
-                  for csr, b in chrom_inputs]
+        for i, (csr, b) in enumerate(chrom_inputs):
+            st = prepare_chrom(csr, b, design, dist_min, dist_max, bias_thresh,
+                               mean_thresh, norm, n_bins)
+            for k in PREPARE_OUTPUTS:
+                emit(i, k, st[k])
+            states.append(st)
     with stage('estimate_disp'):
         dpd, fns, stats = estimate_disp(states, design, dist_max,
                                         estimator=estimator, frac=frac,
                                         auto_frac_factor=auto_frac_factor,
                                         weighted_lowess=weighted_lowess)
+        for i, s in enumerate(states):
+            emit(i, 'disp', s['disp'])
     with stage('lrt'):
-        for s in states:
+        for i, s in enumerate(states):
             lrt_chrom(s, design, refit_mu)
+            for k in LRT_OUTPUTS:
+                emit(i, k, s[k])
     with stage('bh'):
         bh(states)
+        for i, s in enumerate(states):
+            emit(i, 'qvalues', s['qvalues'])
     return states, dpd, fns, stats

@@ -32,6 +32,21 @@ void hc_q2q(const double* x, const double* mu_in, const double* mu_out, double a
 void hc_lgamma_pos(const double* x, int n, double* out) {
     for (int i = 0; i < n; ++i) out[i] = h3d::lgamma_pos(x[i]);
 }
+void hc_fast_log(const double* x, int n, double* out) {
+    h3d::LogTabEntry tab[h3d::kLogTabSize];
+    for (int j = 0; j < h3d::kLogTabSize; ++j) h3d::log_table_entry(j, &tab[j]);
+    for (int i = 0; i < n; ++i) out[i] = h3d::fast_log_pos(x[i], tab);
+}
+// lgamma through the likelihood's Stirling core (shifted): core - x + .5 ln 2pi
+void hc_lgamma_core(const double* x, int n, double* out) {
+    h3d::LogTabEntry tab[h3d::kLogTabSize];
+    for (int j = 0; j < h3d::kLogTabSize; ++j) h3d::log_table_entry(j, &tab[j]);
+    for (int i = 0; i < n; ++i) {
+        double sh;
+        const double c = h3d::stirling_core_shifted(x[i], tab, &sh);
+        out[i] = (c - sh) - x[i] + 0.9189385332046727;
+    }
+}
 void hc_chi2_sf(const double* x, int n, int df, double* out) {
     for (int i = 0; i < n; ++i) out[i] = h3d::chi2_sf(x[i], df);
 }

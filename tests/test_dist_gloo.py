@@ -36,25 +36,30 @@ def _worker(rank, world, port, ret):
         td.all_gather_object(gathered, mine)
         assert sorted(sum(gathered, [])) == sorted(chroms)
         # 2. exchange by distance: every pixel ends on the owner of its
-        # distance, grouped by distance, source ranks in rank order
+        # distance (round robin), grouped by distance, source ranks in order
         rng = np.random.default_rng(100 + rank)
-        n_dist, n_reps, n = 12, 3, 200 + 50 * rank
-        dist = np.sort(rng.integers(2, n_dist, size=n))
-        seg = np.concatenate([[0], np.cumsum(np.bincount(dist, minlength=n_dist))])
+        n_dist, n_reps, n = 13, 3, 200 + 50 * rank
+        key_of_dist, per = hd.distance_keys(n_dist)
+        assert sorted(key_of_dist) == sorted(set(key_of_dist))
+        dist = rng.integers(2, n_dist, size=n)
+        dist = dist[np.argsort(key_of_dist[dist], kind='stable')]   # pooled
+        seg = np.concatenate([[0], np.cumsum(np.bincount(
+            key_of_dist[dist], minlength=per * world))])
         x = np.stack([dist * 1000.0 + rank * 100 + r for r in range(n_reps)])
         ident = rng.random(n)                       # per-pixel tag
         f = np.stack([ident + r for r in range(n_reps)])
-        xo, fo, seg_o, bounds = hd.exchange_by_distance(
+        xo, fo, seg_o = hd.exchange_by_distance(
             torch.from_numpy(x), torch.from_numpy(f), seg, n)
-        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+        mine_d = hd.owned_distances(n_dist)
+        assert len(seg_o) == per + 1
         n_got = int(seg_o[-1])
         xo, fo = xo.numpy()[:, :n_got], fo.numpy()[:, :n_got]
-        for d in range(n_dist):
-            a, b = int(seg_o[d]), int(seg_o[d + 1])
-            if not (lo <= d < hi):
+        for j in range(per):
+            a, b = int(seg_o[j]), int(seg_o[j + 1])
+            if j >= len(mine_d):
                 assert a == b
                 continue
-            assert (xo[0, a:b] // 1000 == d).all()
+            assert (xo[0, a:b] // 1000 == mine_d[j]).all()
             src = (xo[0, a:b] % 1000) // 100
             assert (np.diff(src) >= 0).all()        # rank order inside a distance
         # every pixel arrived exactly once, on exactly one rank
@@ -64,14 +69,14 @@ def _worker(rank, world, port, ret):
         td.all_gather_object(sent, ident.tolist())
         assert sorted(sum(tags, [])) == sorted(sum(sent, []))
         # 3. merge of per-distance dispersions
-        local = np.full((n_dist, 2), np.nan)
-        local[lo:hi] = np.arange(lo, hi)[:, None] + np.array([0.0, 0.5])
-        local[lo:hi][seg_o[lo + 1:hi + 1] - seg_o[lo:hi] == 0] = np.nan
-        merged = hd.merge_disp_per_dist(local, bounds)
-        counts = np.zeros(n_dist)
+        local = np.full((per, 2), np.nan)
+        local[:len(mine_d)] = mine_d[:, None] + np.array([0.0, 0.5])
+        local[np.diff(seg_o) == 0] = np.nan
+        merged = hd.merge_disp_per_dist(local, n_dist)
         allc = [None] * world
         td.all_gather_object(allc, np.bincount(dist, minlength=n_dist).tolist())
         counts = np.sum(allc, axis=0)
+        assert merged.shape == (n_dist, 2)
         assert np.array_equal(np.isnan(merged[:, 0]), counts == 0)
         ok = counts > 0
         assert np.array_equal(merged[ok, 1], np.arange(n_dist)[ok] + 0.5)
@@ -131,7 +136,10 @@ def test_lpt_and_ranges():
     loads = [sum(w for w, o in zip([10, 9, 8, 7, 1, 1], owner) if o == k)
              for k in range(2)]
     assert abs(loads[0] - loads[1]) <= 2
-    b = hd.distance_ranges(np.array([0, 0, 5, 5, 5, 5, 0]), 2)
-    assert b[0] == 0 and b[-1] == 7 and b[1] in (4, 5)
-    b = hd.distance_ranges(np.zeros(5, dtype=int), 3)
-    assert (np.diff(b) >= 0).all() and b[-1] == 5
+    keys, per = hd.distance_keys(201, 8)
+    assert per == 26 and len(set(keys)) == 201 and keys.max() < 8 * per
+    for k in range(8):
+        d = hd.owned_distances(201, k, 8)
+        assert (d % 8 == k).all() and (keys[d] == k * per + np.arange(len(d))).all()
+    keys, per = hd.distance_keys(7, 1)
+    assert per == 7 and (keys == np.arange(7)).all()

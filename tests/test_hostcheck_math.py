@@ -124,3 +124,29 @@ def test_brent_state_machine_matches_scipy(L):
                         ctypes.c_double(100. / 101), ctypes.c_double(1e-5),
                         500, ctypes.byref(nfev), ctypes.byref(flag))
         assert xf == res.x and nfev.value == res.nfev and flag.value == 0
+
+
+def test_table_log_and_stirling_core(L):
+    """the table-driven log of the likelihood kernel and the shifted Stirling
+    log-gamma built on it, against libm / scipy in the ranges the kernel uses
+    (arguments y + r with r in [0.01, 1e4], y in [0, 1e6])"""
+    rng = np.random.default_rng(7)
+    n = 400000
+    x = 10 ** rng.uniform(np.log10(3.0), 7, n)
+    x[:2000] = np.nextafter(2.0 ** rng.integers(2, 20, 2000), 0)   # just below 2^k
+    x[2000:4000] = 2.0 ** rng.integers(2, 20, 2000)
+    out = np.zeros(n)
+    L.hc_fast_log(P(x), n, P(out))
+    ref = np.log(x)
+    ulp = np.abs(out - ref) / np.spacing(ref)
+    assert ulp.max() <= 2.0, ulp.max()
+    xs = np.concatenate([10 ** rng.uniform(-2, 1, 200000),
+                         10 ** rng.uniform(1, 6, 200000)])
+    out = np.zeros(len(xs))
+    L.hc_lgamma_core(P(xs), len(xs), P(out))
+    ref = sp.gammaln(xs)
+    # absolute error in units of the largest intermediate: arguments below 10
+    # are shifted to [10, 11), where (x - .5) ln x ~ 25
+    scale = np.maximum(np.abs(ref), 25.0)
+    # a handful of roundings at that magnitude: under 5 ulp
+    assert (np.abs(out - ref) / scale).max() < 1e-15
