@@ -289,17 +289,22 @@ def main():
         assert len(out) == len(OUTPUT_NAMES) * len(states)
         return states, stats, drain.nbytes
 
+    step_wall = {}
+
     def timed(fn, steps):
         ev0 = torch.cuda.Event(enable_timing=True)
         ev1 = torch.cuda.Event(enable_timing=True)
         sync_all()
+        walls = step_wall.setdefault(fn.__name__, [])
         prof = os.environ.get('H3D_PROFILE') == fn.__name__
         if prof:        # ncu --profile-from-start off: capture this region only
             torch.cuda.profiler.start()
         ev0.record()
         out = None
         for _ in range(steps):
+            t0 = time.perf_counter()
             out = fn()
+            walls.append(round(1e3 * (time.perf_counter() - t0), 2))
         ev1.record()
         sync_all()
         if prof:
@@ -392,6 +397,7 @@ def main():
                       nll_ms=stats['nll_us'] * 1e-3,
                       equalize_ms=stats['equalize_us'] * 1e-3),
             cpu_baseline=cpu,
+            host_ms_per_step=step_wall,
             clocks=sampler.summary())
         print(json.dumps(line))
     if world > 1:

@@ -50,6 +50,7 @@ SIGNATURES = {
                         vp, vp, vp]),
     'h3d_lrt_fused': (c_int, [vp, vp, vp, c_ll, vp, vp, c_int, vp, vp, vp,
                               c_int, c_int, c_int, vp, vp, vp, vp, vp, vp]),
+    'h3d_publish': (c_int, [vp, vp, c_sz, vp]),
     'h3d_bh': (c_int, [vp, c_ll, vp, vp, c_sz, vp]),
     'h3d_bh_ws_bytes': (c_sz, [c_ll]),
     'h3d_bh_ranked': (c_int, [vp, c_ll, c_ll, c_ll, vp, vp, vp, c_sz, vp]),

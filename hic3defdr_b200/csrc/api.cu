@@ -39,9 +39,30 @@ fp64_peak_kernel(double* out, int iters, double a, double b) {
     if (s == 123.456) out[0] = s;      // keeps the chains alive
 }
 
+// small device -> host-visible copy done by the SMs (see h3d_publish)
+__global__ void publish_kernel(const unsigned long long* __restrict__ src,
+                               volatile unsigned long long* __restrict__ dst, int n_words) {
+    for (int i = threadIdx.x; i < n_words; i += blockDim.x) dst[i] = src[i];
+}
+
 }  // namespace h3d
 
 extern "C" {
+
+// Copies ``nbytes`` (a multiple of 8, at most 64 KiB) from device memory to
+// pinned, device-mapped host memory with a kernel instead of the copy engine:
+// small control read-backs (pixel counts, convergence counters) then never
+// queue behind the bulk device->host output copies that share the DMA engine.
+// The data are valid on the host after the stream is synchronised.
+int h3d_publish(const void* dev_src, void* host_mapped_dst, size_t nbytes, h3d_stream_t stream) {
+    H3D_REQUIRE(nbytes % 8 == 0 && nbytes <= 65536, "publish size must be a multiple of 8, <= 64 KiB");
+    if (nbytes == 0) return H3D_OK;
+    h3d::publish_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(
+        (const unsigned long long*)dev_src, (volatile unsigned long long*)host_mapped_dst,
+        (int)(nbytes / 8));
+    H3D_LAUNCHED("publish_kernel");
+    return H3D_OK;
+}
 
 int h3d_version(void) { return 100; }
 

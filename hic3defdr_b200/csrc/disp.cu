@@ -19,6 +19,7 @@
 //                     the qCML stopping rule |delta disp| <= 1e-4
 // FP64-pipe bound: ~44 k FP64 instruction-
 // equivalents per pixel against 16 R_c bytes read + 8 R_c written per sweep.
+#include <string.h>
 #include <vector>
 
 #include "common.cuh"
@@ -370,6 +371,14 @@ __global__ void step_kernel(Problem* __restrict__ prob, const int* __restrict__ 
 
 __global__ void reset_counters_kernel(Counters* cnt) { cnt->n_need_eq = 0; cnt->n_in_brent = 0; }
 
+// device -> pinned, device-mapped host memory by the SMs: the per-round
+// convergence counters (and the final table) must not queue on the copy engine
+// behind bulk output copies of other streams
+__global__ void publish_words_kernel(const unsigned long long* __restrict__ src,
+                                     volatile unsigned long long* __restrict__ dst, int n_words) {
+    for (int i = threadIdx.x; i < n_words; i += blockDim.x) dst[i] = src[i];
+}
+
 __global__ void collect_kernel(const Problem* __restrict__ prob, int n, double* __restrict__ disp_out,
                                long long* __restrict__ stats) {
     // single block
@@ -390,6 +399,22 @@ __global__ void collect_kernel(const Problem* __restrict__ prob, int n, double* 
 }  // namespace h3d
 
 using namespace h3d;
+
+// process-wide pinned scratch for control read-backs (grown on demand; the
+// library is driven by one host thread per process, one process per GPU)
+static void* g_pinned = nullptr;
+static size_t g_pinned_bytes = 0;
+static int pinned_scratch(size_t bytes, void** host, void** dev) {
+    if (bytes > g_pinned_bytes) {
+        if (g_pinned) cudaFreeHost(g_pinned);
+        g_pinned = nullptr; g_pinned_bytes = 0;
+        H3D_CHECK(cudaHostAlloc(&g_pinned, bytes, cudaHostAllocPortable | cudaHostAllocMapped));
+        g_pinned_bytes = bytes;
+    }
+    *host = g_pinned;
+    H3D_CHECK(cudaHostGetDevicePointer(dev, g_pinned, 0));
+    return H3D_OK;
+}
 
 static long long count_chunks(const long long* seg_start_host, int n_seg) {
     long long n = 0;
@@ -489,6 +514,12 @@ extern "C" int h3d_estimate_dispersion(const double* x, const double* f, long lo
     H3D_LAUNCHED("init_problems_kernel");
     const dim3 cgrid(n_chunks, n_conds);
     Counters h_cnt;
+    void *pin_host = nullptr, *pin_dev = nullptr;
+    {
+        int rc = pinned_scratch(256 + (size_t)n_prob * 8 + 64, &pin_host, &pin_dev);
+        if (rc) return rc;
+    }
+    static_assert(sizeof(Counters) == 16, "Counters is published as two 8-byte words");
     const size_t eq_smem = (size_t)kEqTasks * (sizeof(EqTask) + sizeof(int));
     H3D_CHECK(cudaFuncSetAttribute(equalize_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eq_smem));
     H3D_CHECK(cudaFuncSetAttribute(equalize_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eq_smem));
@@ -545,8 +576,11 @@ extern "C" int h3d_estimate_dispersion(const double* x, const double* f, long lo
             step_kernel<<<pgrid, 128, 0, st>>>(prob, seg_chunk_start, partial, partial_cnt, n_chunks, n_seg,
                                                n_conds, estimator, 1, cnt);
             H3D_LAUNCHED("step_kernel");
-            H3D_CHECK(cudaMemcpyAsync(&h_cnt, cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+            publish_words_kernel<<<1, 32, 0, st>>>((const unsigned long long*)cnt,
+                                                   (volatile unsigned long long*)pin_dev, 2);
+            H3D_LAUNCHED("publish_words_kernel");
             H3D_CHECK(cudaStreamSynchronize(st));
+            memcpy(&h_cnt, pin_host, sizeof(Counters));
             {
                 float ms = 0.f;
                 if (did_eq) {
@@ -574,10 +608,17 @@ extern "C" int h3d_estimate_dispersion(const double* x, const double* f, long lo
     for (int k = 0; k < 4; ++k) cudaEventDestroy(ev[k]);
     collect_kernel<<<1, 256, 0, st>>>(prob, n_prob, disp_dev, stats_dev);
     H3D_LAUNCHED("collect_kernel");
-    H3D_CHECK(cudaMemcpyAsync(disp_per_dist_host, disp_dev, (size_t)n_prob * 8, cudaMemcpyDeviceToHost, st));
-    long long h_stats[4] = {0, 0, 0, 0};
-    H3D_CHECK(cudaMemcpyAsync(h_stats, stats_dev, 3 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    // disp_dev and stats_dev are adjacent 256-byte aligned carvings: publish both
+    publish_words_kernel<<<1, 256, 0, st>>>((const unsigned long long*)disp_dev,
+                                            (volatile unsigned long long*)((char*)pin_dev + 256), n_prob);
+    H3D_LAUNCHED("publish_words_kernel");
+    publish_words_kernel<<<1, 32, 0, st>>>((const unsigned long long*)stats_dev,
+                                           (volatile unsigned long long*)((char*)pin_dev + 64), 3);
+    H3D_LAUNCHED("publish_words_kernel");
     H3D_CHECK(cudaStreamSynchronize(st));
+    memcpy(disp_per_dist_host, (char*)pin_host + 256, (size_t)n_prob * 8);
+    long long h_stats[4] = {0, 0, 0, 0};
+    memcpy(h_stats, (char*)pin_host + 64, 3 * sizeof(long long));
     if (stats_host) {
         stats_host[0] = h_stats[0]; stats_host[1] = h_stats[1]; stats_host[2] = h_stats[2];
         stats_host[3] = (long long)(h3d_launch_count() - launches_before);

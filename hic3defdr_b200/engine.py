@@ -87,7 +87,7 @@ def pool_by_distance(states, dist_max):
                     s['row'], s['col'], s['disp_index'], s['raw'],
                     s['size_factors'], s['bias'], rank[o:o + n], x.shape[1],
                     x, f, None)
-        seg_start = key_start.cpu().numpy()
+        seg_start = ops.to_host(key_start)
     else:
         seg_start = np.zeros(n_keys + 1, dtype=np.int64)
     return x, f, dist_cat, seg_start, offs
@@ -150,11 +150,11 @@ def estimate_disp(states, design, dist_max, cond_names=None, estimator='qcml',
     return disp_per_dist, fns, stats
 
 
-def lrt_chrom(st, design, refit_mu=True):
+def lrt_chrom(st, design, refit_mu=True, failed=None):
     """analysis/analysis.py:261-284 for one chromosome state."""
     p, llr, mu0, mu1 = ops.lrt_fused(
         st['row'], st['col'], st['disp_index'], st['raw'], st['size_factors'],
-        st['bias'], st['disp'], design, refit_mu)
+        st['bias'], st['disp'], design, refit_mu, failed)
     st.update(pvalues=p, llr=llr, mu_hat_null=mu0, mu_hat_alt=mu1)
     return st
 
@@ -212,10 +212,12 @@ def run_to_qvalues(chrom_inputs, design, dist_min=4, dist_max=200,
         for i, s in enumerate(states):
             emit(i, 'disp', s['disp'])
     with stage('lrt'):
+        failed = torch.zeros(1, dtype=torch.int32, device='cuda')
         for i, s in enumerate(states):
-            lrt_chrom(s, design, refit_mu)
+            lrt_chrom(s, design, refit_mu, failed)
             for k in LRT_OUTPUTS:
                 emit(i, k, s[k])
+        ops.check_failed(failed, 'lrt')
     with stage('bh'):
         bh(states)
         for i, s in enumerate(states):

@@ -46,8 +46,33 @@ def design_bytes(design):
     return np.ascontiguousarray(np.asarray(design).astype(bool)).view(np.uint8)
 
 
+_MAILBOX = {}
+
+
+def to_host(t):
+    """Small CUDA tensor (<= 64 KiB) -> numpy copy without the copy engine
+    (h3d_publish into a pinned mailbox + a stream synchronisation): control
+    values such as pixel counts must not wait behind bulk output copies."""
+    t = t.contiguous()
+    nbytes = t.numel() * t.element_size()
+    if nbytes == 0:
+        return np.empty(tuple(t.shape), dtype=torch.empty(
+            0, dtype=t.dtype).numpy().dtype)
+    padded = (nbytes + 7) // 8 * 8
+    if padded > 65536 or padded != nbytes:
+        return t.cpu().numpy()
+    dev_i = torch.cuda.current_device()
+    box = _MAILBOX.get(dev_i)
+    if box is None:
+        box = torch.zeros(65536, dtype=torch.uint8).pin_memory()
+        _MAILBOX[dev_i] = box
+    lib().call('h3d_publish', ptr(t), ptr(box), nbytes, _stream())
+    torch.cuda.current_stream().synchronize()
+    return box[:nbytes].view(t.dtype).numpy().reshape(tuple(t.shape)).copy()
+
+
 def _check_failed(counter, what):
-    n = int(counter.item())
+    n = int(to_host(counter.to(torch.int64))[0])
     if n:
         raise AssertionError(
             '%s: %d pixel(s) have no positive root (all-zero counts within a '
@@ -126,7 +151,7 @@ def union_gather(csr, dist_thresh, bias=None):
     lib().call('h3d_union_count', csr.n_reps, ip, csr.is64, ix, dt,
                _DTYPES[csr.dtype], bptr, n, int(dist_thresh), ptr(offs),
                ptr(ws), wsb, _stream())
-    n_px = int(offs[n].item())
+    n_px = int(to_host(offs[n:n + 1].to(torch.int64))[0])
     row = torch.empty(n_px, dtype=torch.int32, device='cuda')
     col = torch.empty_like(row)
     dist = torch.empty_like(row)
@@ -246,7 +271,7 @@ def mask_to_index(mask):
     ws = workspace(wsb)
     lib().call('h3d_mask_to_index', ptr(m), n, ptr(idx), ptr(cnt), ptr(ws),
                wsb, _stream())
-    return idx[:int(cnt.item())]
+    return idx[:int(to_host(cnt)[0])]
 
 
 def loop_membership(row, col, index, pixels):
@@ -397,10 +422,18 @@ def lrt(raw, f, disp, design, refit_mu=True):
     return p, llr, mu0, mu1
 
 
+def check_failed(counter, what):
+    """raises the reference's AssertionError if the device counter of pixels
+    without a positive root is non-zero"""
+    _check_failed(counter, what)
+
+
 def lrt_fused(row, col, index, raw, size_factors, bias, disp, design,
-              refit_mu=True):
+              refit_mu=True, failed=None):
     """The LRT of hic3defdr/analysis/analysis.py:261-278 reading the
-    union-aligned device arrays directly."""
+    union-aligned device arrays directly.  ``failed``: optional int32 device
+    counter shared by several calls; the caller then runs ``check_failed``
+    once (one host synchronisation instead of one per chromosome)."""
     design = np.asarray(design).astype(bool)
     n_reps, n_conds = design.shape
     n = index.numel()
@@ -408,14 +441,17 @@ def lrt_fused(row, col, index, raw, size_factors, bias, disp, design,
     llr = torch.empty_like(p)
     mu0 = torch.empty_like(p)
     mu1 = torch.empty((n, n_conds), dtype=torch.float64, device='cuda')
-    failed = torch.zeros(1, dtype=torch.int32, device='cuda')
+    deferred = failed is not None
+    if not deferred:
+        failed = torch.zeros(1, dtype=torch.int32, device='cuda')
     db = design_bytes(design)
     lib().call('h3d_lrt_fused', ptr(row), ptr(col), ptr(index), n, ptr(raw),
                ptr(size_factors), int(size_factors.dim() == 2), ptr(bias),
                ptr(disp), ptr(db), n_reps, n_conds,
                int(bool(refit_mu)), ptr(p), ptr(llr), ptr(mu0), ptr(mu1),
                ptr(failed), _stream())
-    _check_failed(failed, 'lrt')
+    if not deferred:
+        _check_failed(failed, 'lrt')
     return p, llr, mu0, mu1
 
 

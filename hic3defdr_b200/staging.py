@@ -72,12 +72,24 @@ class InputPrefetcher(object):
 
     def _issue(self, i):
         mats, bias = self.host[i]
+        cur = torch.cuda.current_stream()
+        # device buffers come from the consumer stream's pool (no cross-stream
+        # allocator traffic); the copy stream may fill them once the consumer
+        # stream has passed this point (their previous users are done by then)
+        dev = [{k: torch.empty(v.shape, dtype=v.dtype, device='cuda')
+                for k, v in m.items()} for m in mats]
+        b = torch.empty(bias.shape, dtype=bias.dtype, device='cuda')
+        here = torch.cuda.Event()
+        here.record(cur)
+        self.stream.wait_event(here)
         with torch.cuda.stream(self.stream):
-            csr = csr_to_device(mats, bias.shape[0])
-            b = bias.cuda(non_blocking=True)
+            for m, d in zip(mats, dev):
+                for k, v in m.items():
+                    d[k].copy_(v, non_blocking=True)
+            b.copy_(bias, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self.stream)
-        return csr, b, ev
+        return csr_to_device(dev, bias.shape[0]), b, ev
 
     def __iter__(self):
         pending = []
@@ -91,10 +103,7 @@ class InputPrefetcher(object):
             if nxt < n:
                 pending.append(self._issue(nxt))
                 nxt += 1
-            cur = torch.cuda.current_stream()
-            cur.wait_event(ev)
-            for t in csr.indptr + csr.indices + csr.data + [b]:
-                t.record_stream(cur)       # allocated on the copy stream
+            torch.cuda.current_stream().wait_event(ev)
             self.keep.append((csr, b))
             yield csr, b
 

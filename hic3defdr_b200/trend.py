@@ -115,7 +115,8 @@ def _device_lowess(x, y, frac, delta_frac, it=3):
     lib().call('h3d_lowess', ptr(xd), ptr(yd), n, float(frac), int(it),
                float(delta), ptr(out), ptr(ws), wsb,
                torch.cuda.current_stream().cuda_stream)
-    return x, out.cpu().numpy()
+    from hic3defdr_b200.ops import to_host
+    return x, to_host(out)
 
 
 def lowess_fit(x, y, logx=False, logy=False, left_boundary=None,

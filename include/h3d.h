@@ -213,6 +213,16 @@ int h3d_lrt_fused(const int* row, const int* col, const int* index, long long n_
                   int refit_mu, double* pvalues, double* llr, double* mu_hat_null,
                   double* mu_hat_alt, int* n_failed, h3d_stream_t stream);
 
+/* ---- control read-back --------------------------------------------------- */
+
+/* Copies nbytes (multiple of 8, <= 64 KiB) from device memory to pinned,
+ * device-mapped host memory with a kernel rather than the copy engine, so that
+ * small control read-backs (pixel counts that size the next allocation,
+ * convergence counters) never queue behind bulk output copies on the DMA
+ * engine.  Valid on the host once the stream is synchronised. */
+int h3d_publish(const void* dev_src, void* host_mapped_dst, size_t nbytes,
+                h3d_stream_t stream);
+
 /* ---- bh ----------------------------------------------------------------- */
 
 /* Benjamini-Hochberg q-values over the finite entries of p
