@@ -71,11 +71,11 @@ __global__ void init_problems_kernel(Problem* __restrict__ prob, const long long
 //   1. per pixel: fit_mu, the clamped (mu_in, mu_out) of every replicate;
 //      replicates whose quantile map needs no incomplete gamma function
 //      (x = 0 in the left tail) are finished here, the others become tasks
-//      (x, mu_in, mu_out, destination), right-tail tasks filling the task
-//      array from the front, left-tail tasks from the back;
+//      (x, mu_in, mu_out, destination), tasks whose incomplete gamma function
+//      is evaluated by the continued fraction filling the task array from
+//      the front, power-series tasks from the back;
 //   2. the tasks are processed in array order, so that the lanes of a warp
-//      run the same branch of the incomplete gamma code (continued fraction
-//      for the right tail, series for the left tail) instead of diverging
+//      run the same branch of the incomplete gamma code instead of diverging
 //      per replicate.
 constexpr int kEqTasks = 2048;      // task slots per batch (56 KB of shared memory)
 
@@ -150,8 +150,13 @@ equalize_kernel(const double* __restrict__ x, const double* __restrict__ f, long
                     if (valid && cheap)
                         out_base[(long long)k * ld + i] = q2q_zero(mu_in, mu_out, alpha);
                     const bool push = valid && !cheap;
-                    const unsigned m_r = __ballot_sync(0xffffffffu, push && right);
-                    const unsigned m_l = __ballot_sync(0xffffffffu, push && !right);
+                    // which algorithm the tail evaluations of this task will use
+                    // (FP32 copy of gamma_use_series: only a scheduling hint)
+                    const float rin_f = 1.0f + (float)alpha * (float)mu_in;
+                    const bool front = !gamma_use_series((double)((float)mu_in / rin_f),
+                                                         (double)((float)xr[k] / rin_f));
+                    const unsigned m_r = __ballot_sync(0xffffffffu, push && front);
+                    const unsigned m_l = __ballot_sync(0xffffffffu, push && !front);
                     int base_r = 0, base_l = 0;
                     if (lane == 0) {
                         if (m_r) base_r = atomicAdd(&n_right, __popc(m_r));
@@ -160,7 +165,7 @@ equalize_kernel(const double* __restrict__ x, const double* __restrict__ f, long
                     base_r = __shfl_sync(0xffffffffu, base_r, 0);
                     base_l = __shfl_sync(0xffffffffu, base_l, 0);
                     if (push) {
-                        const int slot = right ? base_r + __popc(m_r & lt_mask)
+                        const int slot = front ? base_r + __popc(m_r & lt_mask)
                                                : kEqTasks - 1 - (base_l + __popc(m_l & lt_mask));
                         task[slot].x = xr[k];
                         task[slot].mu_in = mu_in;
@@ -173,7 +178,7 @@ equalize_kernel(const double* __restrict__ x, const double* __restrict__ f, long
         __syncthreads();
         if (estimator == H3D_EST_CML) continue;
         const int nR = n_right, nL = n_left;
-        // right-tail tasks [0, nR), then left-tail tasks [kEqTasks - nL, kEqTasks)
+        // continued-fraction tasks [0, nR), then series tasks [kEqTasks - nL, kEqTasks)
         for (int t0 = 0; t0 < nR + nL; t0 += 256) {
             const int t = t0 + threadIdx.x;
             if (t < nR + nL) {

@@ -33,6 +33,14 @@ extern H3dStats g_h3d_stats;
 #define H3D_STAT(field) ((void)0)
 #endif
 
+// Halley iteration of the incomplete-gamma inverse: a step smaller than this
+// (in units of the distribution's width, y / sqrt(a)) ends the iteration -- the
+// error left after a step of size e is ~ C e^3 (cubic convergence).  See
+// tests/test_hostcheck_math.py for the accuracy this leaves.
+#ifndef H3D_HALLEY_TOL
+#define H3D_HALLEY_TOL 2e-4
+#endif
+
 namespace h3d {
 
 constexpr int kMaxReps = 16;
@@ -279,8 +287,22 @@ H3D_HD double gamma_cf_factor(double a, double x) {
     return h_prev;
 }
 
+// The power series converges for every x; the continued fraction only pays for
+// itself when x is well above a.  For small x (a handful of counts, the bulk
+// of the far-distance pixels) the fraction needs ~50 steps where the series
+// needs ~30 cheaper terms, so the series also serves the upper tail there as
+// long as the complement 1 - P does not cancel (z-score below kSeriesZMax,
+// i.e. Q > ~0.02: at most ~50 eps relative error in Q).
+#ifndef H3D_SERIES_XMAX
+#define H3D_SERIES_XMAX 6.0
+#endif
+#ifndef H3D_SERIES_ZMAX
+#define H3D_SERIES_ZMAX 1.8
+#endif
 H3D_HD bool gamma_use_series(double a, double x) {
-    return (x < 1.0) || (x < a);
+    if ((x < 1.0) || (x < a)) return true;
+    const double dz = x - a;
+    return (x < H3D_SERIES_XMAX) && (dz * dz < (H3D_SERIES_ZMAX * H3D_SERIES_ZMAX) * a);
 }
 
 // log of the lower (upper = false) or upper tail at y > 0,
@@ -334,6 +356,8 @@ H3D_HD double gamma_log_tail_inv(const GammaShape& s, double lt, bool upper, dou
     if (!(lt < 0.0)) return (lt == 0.0) ? (upper ? 0.0 : INFINITY) : NAN;
     const double a = s.a;
     double lo = 0.0, hi = INFINITY;
+    // the natural unit of a step is the distribution's width, y / sqrt(a)
+    const double step_tol = (a > 1.0) ? H3D_HALLEY_TOL / sqrt(a) : H3D_HALLEY_TOL;
     double y = (guess > 0.0 && isfinite(guess)) ? guess : a;
     if (!upper) {
         // far lower tail: P(a,y) ~ y^a / Gamma(a+1)
@@ -368,7 +392,7 @@ H3D_HD double gamma_log_tail_inv(const GammaShape& s, double lt, bool upper, dou
             }
             // a step this small means nxt is converged to round-off (the next
             // correction would be below 1e-18 relative)
-            if (fabs(nxt - y) <= 1e-6 * fabs(nxt)) return nxt;
+            if (fabs(nxt - y) <= step_tol * fabs(nxt)) return nxt;
         }
         if (!((nxt > lo) && (nxt < hi))) {
             // Newton left the bracket (or was not available): bisect
