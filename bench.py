@@ -356,6 +356,16 @@ def main():
         eq_s = stats['equalize_us'] * 1e-6
         eq_flops = 2.0 * EQUALIZE_INST_EQ_PER_PX * stats['pixel_equalizations']
         achieved = eq_flops / eq_s / 1e12 if eq_s > 0 else None
+        traffic = None
+        try:
+            with open(os.path.join(REPO, 'profiles', 'r01_traffic.json')) as h:
+                tj = json.load(h)['equalize_kernel']
+            # ncu DRAM bytes of the kernel's launches of one single-GPU step of
+            # this workload, per launch (the capture itself is in profiles/)
+            if world == 1 and args.workload == 'mouse10kb':
+                traffic = tj['dram_bytes_per_step'] / tj['launches_per_step']
+        except Exception:
+            pass
         cpu = None
         if not args.no_cpu_baseline:
             n_cpu, dt_cpu = time_oracle(0)
@@ -384,7 +394,7 @@ def main():
                 bound='fp64', kernel='equalize_kernel',
                 achieved=achieved, peak=peak, unit='TFLOP/s',
                 frac=(achieved / peak) if achieved and peak else None,
-                traffic=None,
+                traffic=traffic,
                 model='2 x %.0f FP64 inst-eq per pixel-equalisation '
                       '(SURVEY 8(d)) x %d pixel-equalisations / %.1f ms of '
                       'equalize_kernel (CUDA events, %d launches/step, rank 0); '

@@ -257,19 +257,21 @@ nll_kernel(const double* __restrict__ pseudo, long long ld, const int* __restric
             acc += (t + cst) - stirling_core(z + nrr, tab);
         }
     } else {
+        // uniform shift of every argument by n_shift units (see stirling_core_shifted);
+        // the "- n" terms of the (R_c + 1) shifted log-gammas leave (R_c - 1) n_shift
+        const int n_shift = (int)ceil(10.0 - r);
+        const double cst_s = cst - (double)(nr - 1) * (double)n_shift;
         for (long long i = lo + threadIdx.x; i < hi; i += 256) {
-            double z = 0.0, t = 0.0, sh_n = 0.0, n1;
+            double z = 0.0, t = 0.0;
 #pragma unroll
             for (int k = 0; k < MAXRC; ++k) {
                 if (k < nr) {
                     const double y = base[(long long)k * ld + i];
                     z += y;
-                    t += stirling_core_shifted(y + r, tab, &n1);
-                    sh_n += n1;
+                    t += stirling_core_shifted(y + r, n_shift, tab);
                 }
             }
-            const double tX = stirling_core_shifted(z + nrr, tab, &n1);
-            acc += ((t - tX) + cst) - (sh_n - n1);
+            acc += (t + cst_s) - stirling_core_shifted(z + nrr, n_shift, tab);
         }
     }
     const double tot = block_sum_256(acc, sh);

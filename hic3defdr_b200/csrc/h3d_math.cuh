@@ -67,6 +67,18 @@ H3D_HDN double m_log1p(double x) { return log1p(x); }
 struct LogTabEntry { double c, neg_log_c; };
 constexpr int kLogTabSize = 128;
 
+// Polynomial coefficients of the likelihood kernel's hot loop.  In device code
+// they are read as constant-bank operands of the FP64 instructions themselves;
+// as literals the compiler materialises each one with a pair of uniform-register
+// moves in front of its use (66 of the 213 instructions of the loop, ncu r01e),
+// which costs issue slots the FP64 pipe is waiting for.
+#ifdef __CUDACC__
+static __constant__ double kDevLogPoly[6] = {1.0 / 7.0, -1.0 / 6.0, 1.0 / 5.0, -1.0 / 4.0, 1.0 / 3.0, -0.5};
+static __constant__ double kDevStirling[7] = {1.0 / 12.0, -1.0 / 360.0, 1.0 / 1260.0, -1.0 / 1680.0,
+                                              1.0 / 1188.0, -691.0 / 360360.0, 1.0 / 156.0};
+static __constant__ double kDevLn2[2] = {0.693147180559945286, 2.319046813846299616e-17};
+#endif
+
 H3D_HD void log_table_entry(int j, LogTabEntry* e) {
     const double c = 1.0 / (1.0 + ((double)j + 0.5) / (double)kLogTabSize);
     e->c = c;
@@ -89,6 +101,15 @@ H3D_HD double fast_log_pos(double x, const LogTabEntry* tab) {
     const LogTabEntry t = tab[(hi >> 13) & (kLogTabSize - 1)];
     const double r = fma(m, t.c, -1.0);
     const double e = (double)ex;
+#ifdef __CUDA_ARCH__
+    double p = fma(r, kDevLogPoly[0], kDevLogPoly[1]);
+    p = fma(p, r, kDevLogPoly[2]);
+    p = fma(p, r, kDevLogPoly[3]);
+    p = fma(p, r, kDevLogPoly[4]);
+    p = fma(p, r, kDevLogPoly[5]);
+    const double tail = fma(r * r, p, e * kDevLn2[1]);                    // + e ln2_lo
+    return fma(e, kDevLn2[0], t.neg_log_c) + (r + tail);
+#else
     double p = fma(r, 1.0 / 7.0, -1.0 / 6.0);
     p = fma(p, r, 1.0 / 5.0);
     p = fma(p, r, -1.0 / 4.0);
@@ -96,6 +117,7 @@ H3D_HD double fast_log_pos(double x, const LogTabEntry* tab) {
     p = fma(p, r, -0.5);
     const double tail = fma(r * r, p, e * 2.319046813846299616e-17);      // + e ln2_lo
     return fma(e, 0.693147180559945286, t.neg_log_c) + (r + tail);
+#endif
 }
 
 // reciprocal of a positive normal number to ~1 ulp (not correctly rounded):
@@ -514,25 +536,34 @@ H3D_HD double stirling_corr(double x) {
 H3D_HD double stirling_core(double x, const LogTabEntry* tab) {
     const double ix = fast_rcp_pos(x);
     const double ix2 = ix * ix;
+#ifdef __CUDA_ARCH__
+    double c = fma(ix2, kDevStirling[6], kDevStirling[5]);
+    c = fma(ix2, c, kDevStirling[4]);
+    c = fma(ix2, c, kDevStirling[3]);
+    c = fma(ix2, c, kDevStirling[2]);
+    c = fma(ix2, c, kDevStirling[1]);
+    c = fma(ix2, c, kDevStirling[0]);
+    const double corr = ix * c;
+#else
     const double corr = ix * (1.0 / 12.0 + ix2 * (-1.0 / 360.0 + ix2 * (1.0 / 1260.0 +
         ix2 * (-1.0 / 1680.0 + ix2 * (1.0 / 1188.0 + ix2 * (-691.0 / 360360.0 +
         ix2 * (1.0 / 156.0)))))));
+#endif
     return fma(x - 0.5, fast_log_pos(x, tab), corr);
 }
 
-// the same for any x > 0: arguments below 10 are shifted up by the recurrence,
-// log Gamma(x) = log Gamma(x + n) - ln(x (x+1) ... (x+n-1)); returns the core
-// of the shifted argument minus the log of the product and reports the shift n
-// (the caller accounts for the "- x" term: core(x + n) - (x + n) + ...)
-H3D_HD double stirling_core_shifted(double x, const LogTabEntry* tab, double* shifted_by) {
-    double p = 1.0, n = 0.0;
-#pragma unroll
-    for (int k = 0; k < 10; ++k) {
-        if (x < 10.0) { p *= x; x += 1.0; n += 1.0; }
-    }
-    *shifted_by = n;
-    // p >= 1 is not guaranteed (x < 1), and ln p may be near 0: general log
-    return stirling_core(x, tab) - ((n > 0.0) ? log(p) : 0.0);
+// the same for arguments that may be below 10: ALL arguments of a likelihood
+// evaluation are shifted up by the same n = ceil(10 - r) >= 1 unit steps (r > 0
+// is the smallest possible argument, so x + n >= 10 for every pixel):
+//   log Gamma(x) = log Gamma(x + n) - ln(x (x+1) ... (x+n-1)).
+// A uniform n keeps the loop trip count identical across a thread block (no
+// predication) and makes the "- n" terms a per-evaluation constant.  The
+// product is >= r (r+1) ... (r+n-1) >= 3.7e3 for r >= 0.0101 (delta <= 100/101),
+// i.e. far from 1, where the table logarithm is accurate.
+H3D_HD double stirling_core_shifted(double x, int n, const LogTabEntry* tab) {
+    double p = x, xs = x + 1.0;
+    for (int k = 1; k < n; ++k) { p *= xs; xs += 1.0; }
+    return stirling_core(xs, tab) - fast_log_pos(p, tab);
 }
 
 H3D_HD double lgamma_pos(double x) {

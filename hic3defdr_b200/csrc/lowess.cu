@@ -6,112 +6,124 @@
 // _smoothers_lowess.pyx; neither is vendored, the algorithm is Cleveland's:
 // k nearest neighbours, tricube kernel, local linear fit, ``it`` bisquare
 // robustifying passes, ``delta`` skipping with linear interpolation).
-// The problem is tiny (at most a few thousand duplicated points), the anchor
-// sequence is data dependent and serial; the block parallelises the sums
-// inside each local regression and the median of the residuals.
+// The problem is tiny (at most a few thousand duplicated points): one block;
+// the anchor sequence is planned once, the local regressions of a pass run
+// one warp per anchor, the median of the residuals by rank counting.
 #include "common.cuh"
 
 namespace h3d {
 
 constexpr int kLwThreads = 512;
 
-__device__ __forceinline__ double block_reduce_sum(double v, double* sh) {
-    // deterministic: warp shuffle tree then thread 0 adds the warp sums in order
-    v = warp_sum(v);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double t = 0.0;
-    for (int w = 0; w < kLwThreads / 32; ++w) t += sh[w];
-    return t;
+// Which points get their own local regression ("anchors") depends on x alone
+// (the delta rule and the ties), not on y or on the robustness weights.  The
+// kernel therefore walks the anchor sequence once (serially, thread 0), and
+// every robustifying pass then fits all anchors in parallel, one warp per
+// anchor, and fills the skipped / tied points from the recorded plan.
+struct LowessPlan {
+    int* anchor;        // [3 * n]: i, left, right of every anchor
+    int* a0;            // [n] anchor supplying the value (or the left end of the interpolation)
+    int* a1;            // [n] anchor at the right end of the interpolation, -1: copy a0
+    double* al;         // [n] interpolation weight of a1
+};
+
+__device__ __forceinline__ double warp_sum_all(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
 }
 
 __global__ void __launch_bounds__(kLwThreads)
 lowess_kernel(const double* __restrict__ x, const double* __restrict__ y, int n, int k_nn, int n_pass,
               double delta, double* __restrict__ y_fit, double* __restrict__ resid_w,
-              double* __restrict__ resid, double* __restrict__ wbuf) {
-    __shared__ double sh[kLwThreads / 32];
-    __shared__ int s_i, s_last, s_left, s_right, s_done;
+              double* __restrict__ resid, double* __restrict__ fitv, LowessPlan plan) {
+    __shared__ int s_n_anchor;
     __shared__ double s_med[2];
-    const int t = threadIdx.x;
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
     for (int j = t; j < n; j += kLwThreads) resid_w[j] = 1.0;
-    __syncthreads();
-    for (int pass = 0; pass < n_pass; ++pass) {
-        for (int j = t; j < n; j += kLwThreads) y_fit[j] = 0.0;
-        if (t == 0) { s_i = 0; s_last = -1; s_left = 0; s_right = k_nn; s_done = 0; }
-        __syncthreads();
-        while (!s_done) {
-            if (t == 0) {
-                int l = s_left, r = s_right;
-                const double xi = x[s_i];
-                while (r < n && (xi - x[l]) > (x[r] - xi)) { ++l; ++r; }
-                s_left = l; s_right = r;
+    if (t == 0) {
+        // the anchor walk of Cleveland's lowess with delta skipping
+        int i = 0, last = -1, left = 0, right = k_nn, na = 0;
+        while (true) {
+            const double xi = x[i];
+            while (right < n && (xi - x[left]) > (x[right] - xi)) { ++left; ++right; }
+            plan.anchor[3 * na] = i; plan.anchor[3 * na + 1] = left; plan.anchor[3 * na + 2] = right;
+            if (last < i - 1) {                      // points skipped because of delta: interpolate
+                const double a = xi - x[last];
+                const int prev = plan.a0[last];      // the anchor whose value y_fit[last] holds
+                for (int j = last + 1; j < i; ++j) {
+                    plan.a0[j] = prev; plan.a1[j] = na;
+                    plan.al[j] = (x[j] - x[last]) / a;
+                }
             }
-            __syncthreads();
-            const int i = s_i, left = s_left, right = s_right;
+            plan.a0[i] = na; plan.a1[i] = -1;
+            last = i;
+            const double cut = x[last] + delta;
+            int kk;
+            bool stopped = false;
+            for (kk = last + 1; kk < n; ++kk) {
+                if (x[kk] > cut) { stopped = true; break; }
+                if (x[kk] == x[last]) { plan.a0[kk] = na; plan.a1[kk] = -1; last = kk; }   // ties copy the fit
+            }
+            if (!stopped) kk = n - 1;
+            ++na;
+            if (last >= n - 1) break;
+            i = (kk - 1 > last + 1) ? kk - 1 : last + 1;
+        }
+        s_n_anchor = na;
+    }
+    __syncthreads();
+    const int n_anchor = s_n_anchor;
+    for (int pass = 0; pass < n_pass; ++pass) {
+        for (int a = wid; a < n_anchor; a += kLwThreads / 32) {
+            const int i = plan.anchor[3 * a], left = plan.anchor[3 * a + 1], right = plan.anchor[3 * a + 2];
             const double xi = x[i];
             const double radius = fmax(xi - x[left], x[right - 1] - xi);
             // tricube weights times robustness weights
             double part = 0.0;
-            for (int j = left + t; j < right; j += kLwThreads) {
+            for (int j = left + lane; j < right; j += 32) {
                 const double u = fabs(x[j] - xi) / radius;
                 const double c = 1.0 - u * u * u;
-                const double w = c * c * c * resid_w[j];
-                wbuf[j] = w;
-                part += w;
+                part += c * c * c * resid_w[j];
             }
-            const double sw = block_reduce_sum(part, sh);
+            const double sw = warp_sum_all(part);
             double fit;
             if (!(sw > 0.0)) {
                 fit = y[i];
             } else {
-                part = 0.0;
-                for (int j = left + t; j < right; j += kLwThreads) {
-                    const double w = wbuf[j] / sw;
-                    wbuf[j] = w;
-                    part += w * x[j];
+                double p1 = 0.0;
+                for (int j = left + lane; j < right; j += 32) {
+                    const double u = fabs(x[j] - xi) / radius;
+                    const double c = 1.0 - u * u * u;
+                    p1 += (c * c * c * resid_w[j] / sw) * x[j];
                 }
-                const double xbar = block_reduce_sum(part, sh);
-                part = 0.0;
-                for (int j = left + t; j < right; j += kLwThreads) {
+                const double xbar = warp_sum_all(p1);
+                double p2 = 0.0;
+                for (int j = left + lane; j < right; j += 32) {
+                    const double u = fabs(x[j] - xi) / radius;
+                    const double c = 1.0 - u * u * u;
                     const double dx = x[j] - xbar;
-                    part += wbuf[j] * dx * dx;
+                    p2 += (c * c * c * resid_w[j] / sw) * dx * dx;
                 }
-                const double sq = block_reduce_sum(part, sh);
-                part = 0.0;
-                for (int j = left + t; j < right; j += kLwThreads) {
-                    const double p = wbuf[j] * (1.0 + (xi - xbar) * (x[j] - xbar) / sq);
-                    part += p * y[j];
+                const double sq = warp_sum_all(p2);
+                double p3 = 0.0;
+                for (int j = left + lane; j < right; j += 32) {
+                    const double u = fabs(x[j] - xi) / radius;
+                    const double c = 1.0 - u * u * u;
+                    const double w = c * c * c * resid_w[j] / sw;
+                    p3 += w * (1.0 + (xi - xbar) * (x[j] - xbar) / sq) * y[j];
                 }
-                fit = block_reduce_sum(part, sh);
+                fit = warp_sum_all(p3);
             }
-            __syncthreads();
-            if (t == 0) {
-                y_fit[i] = fit;
-                int last = s_last;
-                if (last < i - 1) {                      // anchors skipped because of delta
-                    const double a = xi - x[last];
-                    for (int j = last + 1; j < i; ++j) {
-                        const double al = (x[j] - x[last]) / a;
-                        y_fit[j] = al * fit + (1.0 - al) * y_fit[last];
-                    }
-                }
-                last = i;
-                const double cut = x[last] + delta;
-                int kk = last + 1;
-                bool stopped = false;
-                for (kk = last + 1; kk < n; ++kk) {
-                    if (x[kk] > cut) { stopped = true; break; }
-                    if (x[kk] == x[last]) { y_fit[kk] = y_fit[last]; last = kk; }
-                }
-                if (!stopped) kk = n - 1;
-                const int nxt = (kk - 1 > last + 1) ? kk - 1 : last + 1;
-                s_last = last;
-                s_i = nxt;
-                if (last >= n - 1) s_done = 1;
-            }
-            __syncthreads();
+            if (lane == 0) fitv[a] = fit;
         }
+        __syncthreads();
+        for (int j = t; j < n; j += kLwThreads) {
+            const int b = plan.a1[j];
+            const double v0 = fitv[plan.a0[j]];
+            y_fit[j] = (b < 0) ? v0 : plan.al[j] * fitv[b] + (1.0 - plan.al[j]) * v0;
+        }
+        __syncthreads();
         if (pass < n_pass - 1) {
             // bisquare robustness weights from |resid| / (6 median|resid|)
             for (int j = t; j < n; j += kLwThreads) resid[j] = fabs(y[j] - y_fit[j]);
@@ -143,7 +155,7 @@ lowess_kernel(const double* __restrict__ x, const double* __restrict__ y, int n,
 
 using namespace h3d;
 
-extern "C" size_t h3d_lowess_ws_bytes(int n) { return 3 * ws_pad((size_t)n * 8); }
+extern "C" size_t h3d_lowess_ws_bytes(int n) { return 4 * ws_pad((size_t)n * 8) + ws_pad((size_t)n * 12) + 2 * ws_pad((size_t)n * 4); }
 
 extern "C" int h3d_lowess(const double* x, const double* y, int n, double frac, int it, double delta,
                           double* y_fit, void* ws, size_t ws_bytes, h3d_stream_t stream) {
@@ -152,13 +164,21 @@ extern "C" int h3d_lowess(const double* x, const double* y, int n, double frac, 
     Workspace w(ws, ws_bytes);
     double* resid_w = w.take<double>(n);
     double* resid = w.take<double>(n);
-    double* wbuf = w.take<double>(n);
-    if (!resid_w || !resid || !wbuf) { set_error("lowess workspace too small"); return H3D_ERR_WORKSPACE; }
+    double* fitv = w.take<double>(n);
+    LowessPlan plan;
+    plan.al = w.take<double>(n);
+    plan.anchor = w.take<int>((size_t)3 * n);
+    plan.a0 = w.take<int>(n);
+    plan.a1 = w.take<int>(n);
+    if (!resid_w || !resid || !fitv || !plan.al || !plan.anchor || !plan.a0 || !plan.a1) {
+        set_error("lowess workspace too small");
+        return H3D_ERR_WORKSPACE;
+    }
     int k = (int)(frac * (double)n + 1e-10);
     if (k < 2) k = 2;
     if (k > n) k = n;
     lowess_kernel<<<1, kLwThreads, 0, (cudaStream_t)stream>>>(x, y, n, k, it + 1, delta, y_fit, resid_w,
-                                                             resid, wbuf);
+                                                             resid, fitv, plan);
     H3D_LAUNCHED("lowess_kernel");
     return H3D_OK;
 }

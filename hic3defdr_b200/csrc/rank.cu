@@ -38,6 +38,10 @@ static RankPlan make_rank_plan(long long n, int n_keys) {
     p.n = n; p.n_keys = n_keys;
     long long t = 2048;
     const long long budget = 96LL << 20;     // bytes for the segment x key table
+    // one warp per segment: keep >= 32 warps per SM in flight for small inputs
+    // (a chromosome is 2-5 M pixels), as long as the table stays small
+    while (t > 256 && (n + t - 1) / t < (long long)kNumSMs * 32 &&
+           (n + t / 2 - 1) / (t / 2) * (long long)n_keys * 4 <= (8LL << 20)) t /= 2;
     while ((n + t - 1) / t * (long long)n_keys * 4 > budget) t *= 2;
     p.seg_len = (int)t;
     p.n_segs = (int)((n + t - 1) / t);
@@ -357,21 +361,27 @@ sf_table_kernel(const double* __restrict__ red, const long long* __restrict__ gs
     __shared__ int n_occ;
     const int t = threadIdx.x;
     const bool scaling = (norm == H3D_NORM_CONDITIONAL_SCALING || norm == H3D_NORM_SIMPLE_SCALING);
+    // mean distance of every group (scaling.py:94): exact integer sum / count;
+    // one thread per group, written to the (still uncompacted) slot g of d_b
+    for (int g = t; g < n_groups; g += blockDim.x) {
+        const long long lo = gstart[g], hi = gstart[g + 1];
+        long long sumd = 0;
+        if (key_start && hi > lo) {
+            for (int d = 0; d <= dist_max; ++d) {
+                const long long a = key_start[d] > lo ? key_start[d] : lo;
+                const long long b = key_start[d + 1] < hi ? key_start[d + 1] : hi;
+                if (b > a) sumd += (long long)d * (b - a);
+            }
+        }
+        d_b[g] = (hi > lo) ? (double)sumd / (double)(hi - lo) : 0.0;     // compacted in place below (k <= g)
+    }
+    __syncthreads();
     if (t == 0) {
         int k = 0;
         for (int g = 0; g < n_groups; ++g) {
             const long long lo = gstart[g], hi = gstart[g + 1];
             if (hi <= lo) continue;                       // np.unique(bins): occupied bins only
-            // mean distance of the group (scaling.py:94): exact integer sum / count
-            long long sumd = 0;
-            if (key_start) {
-                for (int d = 0; d <= dist_max; ++d) {
-                    const long long a = key_start[d] > lo ? key_start[d] : lo;
-                    const long long b = key_start[d + 1] < hi ? key_start[d + 1] : hi;
-                    if (b > a) sumd += (long long)d * (b - a);
-                }
-            }
-            d_b[k] = (double)sumd / (double)(hi - lo);
+            d_b[k] = d_b[g];
             if (scaling) {
                 // simple_scaling: s / gmean(s) with pseudocount 1 (scaling.py:64-65)
                 double sl = 0.0;

@@ -93,6 +93,9 @@ def pool_by_distance(states, dist_max):
     return x, f, dist_cat, seg_start, offs
 
 
+_TREND_STREAMS = {}
+
+
 def fit_trends(disp_per_dist, dist_max, cond_names, frac=None,
                auto_frac_factor=15., weighted_lowess=True, log=None):
     """analysis/analysis.py:208-218: one trend per condition; returns
@@ -100,11 +103,10 @@ def fit_trends(disp_per_dist, dist_max, cond_names, frac=None,
     lowess_fn = weighted_lowess_fit if weighted_lowess else lowess_fit
     n_conds = disp_per_dist.shape[1]
     table = np.full((dist_max + 1, n_conds), np.nan)
-    fns = []
-    for c in range(n_conds):
-        if log:
-            log('  estimating dispersion for condition %s' % cond_names[c])
-            log('  fitting distance vs dispersion relationship')
+    device = torch.cuda.current_device()
+
+    def fit_one(c):
+        torch.cuda.set_device(device)        # the current device is per thread
         idx = np.isfinite(disp_per_dist[:, c])
         xs = np.arange(dist_max + 1)[idx]
         ys = disp_per_dist[:, c][idx]
@@ -113,8 +115,29 @@ def fit_trends(disp_per_dist, dist_max, cond_names, frac=None,
             kwargs['frac'] = frac
         if weighted_lowess:
             kwargs['auto_frac_factor'] = auto_frac_factor
-        fn = lowess_fn(xs, ys, **kwargs)
-        table[:, c] = fn(np.arange(dist_max + 1))
+        # own stream: the (latency-bound) smoothing kernels of the conditions
+        # overlap instead of queueing behind each other
+        key = (device, c)
+        if key not in _TREND_STREAMS:       # persistent: their allocator pools stay warm
+            _TREND_STREAMS[key] = torch.cuda.Stream()
+        with torch.cuda.stream(_TREND_STREAMS[key]):
+            fn = lowess_fn(xs, ys, **kwargs)
+        return fn, fn(np.arange(dist_max + 1))
+
+    if log:
+        for c in range(n_conds):
+            log('  estimating dispersion for condition %s' % cond_names[c])
+            log('  fitting distance vs dispersion relationship')
+    torch.cuda.current_stream().synchronize()
+    if n_conds > 1:
+        import concurrent.futures
+        with concurrent.futures.ThreadPoolExecutor(n_conds) as pool:
+            results = list(pool.map(fit_one, range(n_conds)))
+    else:
+        results = [fit_one(0)]
+    fns = []
+    for c, (fn, col) in enumerate(results):
+        table[:, c] = col
         fns.append(fn)
     return fns, table
 

@@ -42,9 +42,12 @@ void hc_lgamma_core(const double* x, int n, double* out) {
     h3d::LogTabEntry tab[h3d::kLogTabSize];
     for (int j = 0; j < h3d::kLogTabSize; ++j) h3d::log_table_entry(j, &tab[j]);
     for (int i = 0; i < n; ++i) {
-        double sh;
-        const double c = h3d::stirling_core_shifted(x[i], tab, &sh);
-        out[i] = (c - sh) - x[i] + 0.9189385332046727;
+        // the kernel shifts by ceil(10 - r) with r <= x the smallest argument of
+        // the evaluation; here: the smallest shift that brings x itself to >= 10
+        const int sh = (x[i] < 10.0) ? (int)ceil(10.0 - x[i]) : 0;
+        const double c = (sh > 0) ? h3d::stirling_core_shifted(x[i], sh, tab)
+                                  : h3d::stirling_core(x[i], tab);
+        out[i] = (c - (double)sh) - x[i] + 0.9189385332046727;
     }
 }
 void hc_chi2_sf(const double* x, int n, int df, double* out) {
