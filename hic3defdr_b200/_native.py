@@ -6,7 +6,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libh3d.so')
+# H3D_LIB selects an alternative build of the same library (A/B measurements)
+LIB_PATH = os.environ.get('H3D_LIB') or os.path.join(HERE, 'libh3d.so')
 
 c_int, c_ll, c_dbl, c_sz = ctypes.c_int, ctypes.c_longlong, ctypes.c_double, \
     ctypes.c_size_t

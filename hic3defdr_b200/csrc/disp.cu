@@ -77,12 +77,21 @@ __global__ void init_problems_kernel(Problem* __restrict__ prob, const long long
 //   2. the tasks are processed in array order, so that the lanes of a warp
 //      run the same branch of the incomplete gamma code instead of diverging
 //      per replicate.
-constexpr int kEqTasks = 2048;      // task slots per batch (56 KB of shared memory)
+#ifndef H3D_EQ_TASKS
+#define H3D_EQ_TASKS 512
+#endif
+constexpr int kEqTasks = H3D_EQ_TASKS;      // task slots per batch (28 B of shared memory each)
 
 struct EqTask { double x, mu_in, mu_out; };
 
+// 4 resident CTAs per SM (<= 64 registers, a few spilled words) beat 3 without
+// spills by 18 %: the kernel waits on dependent FP64 latency, and 32 warps hide
+// more of it than 24 (A/B on B200: 105 -> 87 ms per step; 5 CTAs: 92 ms).
+#ifndef H3D_EQ_MIN_BLOCKS
+#define H3D_EQ_MIN_BLOCKS 4
+#endif
 template <int MAXRC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, H3D_EQ_MIN_BLOCKS)
 equalize_kernel(const double* __restrict__ x, const double* __restrict__ f, long long ld,
                 const int* __restrict__ chunk_seg, const long long* __restrict__ chunk_lo,
                 const long long* __restrict__ seg_start, CondReps cr, int estimator,
@@ -205,10 +214,6 @@ __device__ __forceinline__ double block_sum_256(double v, double* sh) {
     return t;
 }
 
-__global__ void logtab_init_kernel(LogTabEntry* __restrict__ tab) {
-    if (threadIdx.x < kLogTabSize) log_table_entry(threadIdx.x, &tab[threadIdx.x]);
-}
-
 // conditional NB negative log-likelihood partials (dispersion.py:72-75):
 //   sum_px [ sum_k lgamma(y_k + r) + lgamma(n r) - lgamma(z + n r) - n lgamma(r) ]
 // Every log-gamma goes through Stirling's series at an argument >= 10
@@ -222,16 +227,12 @@ template <int MAXRC>
 __global__ void __launch_bounds__(256)
 nll_kernel(const double* __restrict__ pseudo, long long ld, const int* __restrict__ chunk_seg,
            const long long* __restrict__ chunk_lo, const long long* __restrict__ seg_start,
-           CondReps cr, const Problem* __restrict__ prob, const LogTabEntry* __restrict__ logtab,
-           double* __restrict__ partial, int n_chunks) {
+           CondReps cr, const Problem* __restrict__ prob, double* __restrict__ partial, int n_chunks) {
     __shared__ double sh[8];
-    __shared__ LogTabEntry tab[kLogTabSize];
     const int c = blockIdx.y;
     const int s = chunk_seg[blockIdx.x];
     const Problem& q = prob[s * cr.n_conds + c];
     if (q.status != ST_IN_BRENT) return;
-    if (threadIdx.x < kLogTabSize) tab[threadIdx.x] = logtab[threadIdx.x];
-    __syncthreads();
     const double delta = q.brent.x_eval;
     const double r = 1.0 / delta - 1.0;
     const int nr = cr.n_in[c];
@@ -251,10 +252,10 @@ nll_kernel(const double* __restrict__ pseudo, long long ld, const int* __restric
                 if (k < nr) {
                     const double y = base[(long long)k * ld + i];
                     z += y;
-                    t += stirling_core(y + r, tab);
+                    t += stirling_core(y + r);
                 }
             }
-            acc += (t + cst) - stirling_core(z + nrr, tab);
+            acc += (t + cst) - stirling_core(z + nrr);
         }
     } else {
         // uniform shift of every argument by n_shift units (see stirling_core_shifted);
@@ -268,10 +269,10 @@ nll_kernel(const double* __restrict__ pseudo, long long ld, const int* __restric
                 if (k < nr) {
                     const double y = base[(long long)k * ld + i];
                     z += y;
-                    t += stirling_core_shifted(y + r, n_shift, tab);
+                    t += stirling_core_shifted(y + r, n_shift);
                 }
             }
-            acc += (t + cst_s) - stirling_core_shifted(z + nrr, n_shift, tab);
+            acc += (t + cst_s) - stirling_core_shifted(z + nrr, n_shift);
         }
     }
     const double tot = block_sum_256(acc, sh);
@@ -438,7 +439,6 @@ extern "C" size_t h3d_estimate_dispersion_ws_bytes(long long n_px, int n_seg, in
     b += ws_pad((size_t)(n_seg + 1) * 8) + ws_pad((size_t)(n_seg + 1) * 4);
     b += ws_pad((size_t)n_seg * n_conds * sizeof(Problem));
     b += ws_pad((size_t)n_seg * n_conds * 8) + ws_pad(64) + ws_pad(64);
-    b += ws_pad((size_t)kLogTabSize * sizeof(LogTabEntry));
     return b;
 }
 
@@ -501,8 +501,7 @@ extern "C" int h3d_estimate_dispersion(const double* x, const double* f, long lo
     double* disp_dev = w.take<double>(n_prob);
     Counters* cnt = w.take<Counters>(1);
     long long* stats_dev = w.take<long long>(4);
-    LogTabEntry* logtab = w.take<LogTabEntry>(kLogTabSize);
-    if (!logtab || !partial || !partial_cnt || !chunk_seg || !chunk_lo || !seg_start ||
+    if ( !partial || !partial_cnt || !chunk_seg || !chunk_lo || !seg_start ||
         !seg_chunk_start || !prob || !disp_dev || !cnt || !stats_dev) {
         set_error("estimate_dispersion workspace too small (%zu bytes given)", ws_bytes);
         return H3D_ERR_WORKSPACE;
@@ -514,8 +513,6 @@ extern "C" int h3d_estimate_dispersion(const double* x, const double* f, long lo
     // the host vectors must outlive the async copies
     H3D_CHECK(cudaStreamSynchronize(st));
 
-    logtab_init_kernel<<<1, kLogTabSize, 0, st>>>(logtab);
-    H3D_LAUNCHED("logtab_init_kernel");
     const int pgrid = div_up(n_prob, 128);
     init_problems_kernel<<<pgrid, 128, 0, st>>>(prob, seg_start, n_seg, n_conds, estimator, cnt);
     H3D_LAUNCHED("init_problems_kernel");
@@ -573,7 +570,7 @@ extern "C" int h3d_estimate_dispersion(const double* x, const double* f, long lo
             }
             H3D_CHECK(cudaEventRecord(ev[2], st));
 #define CALL(M) nll_kernel<M><<<cgrid, 256, 0, st>>>(pseudo, ld, chunk_seg, chunk_lo, seg_start, cr, prob, \
-        logtab, partial, n_chunks)
+        partial, n_chunks)
             DISPATCH_RC(CALL)
 #undef CALL
             H3D_LAUNCHED("nll_kernel");

@@ -50,7 +50,6 @@ constexpr double kEps = 2.220446049250313e-16;
 // special-function code calls from many places: inlined, they made up 40 % of
 // equalize_kernel's 77 KB of SASS and the warps starved on instruction fetch
 // (ncu: stall "no instruction" dominant).
-H3D_HDN double m_log(double x) { return log(x); }
 H3D_HDN double m_exp(double x) { return exp(x); }
 H3D_HDN double m_log1p(double x) { return log1p(x); }
 
@@ -77,15 +76,17 @@ static __constant__ double kDevLogPoly[6] = {1.0 / 7.0, -1.0 / 6.0, 1.0 / 5.0, -
 static __constant__ double kDevStirling[7] = {1.0 / 12.0, -1.0 / 360.0, 1.0 / 1260.0, -1.0 / 1680.0,
                                               1.0 / 1188.0, -691.0 / 360360.0, 1.0 / 156.0};
 static __constant__ double kDevLn2[2] = {0.693147180559945286, 2.319046813846299616e-17};
+// the table itself: 2 KB, read through L1 (a divergent index would serialise
+// in the constant cache)
+static __device__ const LogTabEntry kDevLogTab[kLogTabSize] = {
+#include "h3d_logtab.inc"
+};
 #endif
+static const LogTabEntry kHostLogTab[kLogTabSize] = {
+#include "h3d_logtab.inc"
+};
 
-H3D_HD void log_table_entry(int j, LogTabEntry* e) {
-    const double c = 1.0 / (1.0 + ((double)j + 0.5) / (double)kLogTabSize);
-    e->c = c;
-    e->neg_log_c = -log(c);
-}
-
-H3D_HD double fast_log_pos(double x, const LogTabEntry* tab) {
+H3D_HD double fast_log_pos(double x) {
 #ifdef __CUDA_ARCH__
     const int hi = __double2hiint(x), lo = __double2loint(x);
     const double m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, lo);
@@ -98,7 +99,13 @@ H3D_HD double fast_log_pos(double x, const LogTabEntry* tab) {
     memcpy(&m, &mb, 8);
 #endif
     const int ex = (hi >> 20) - 1023;
-    const LogTabEntry t = tab[(hi >> 13) & (kLogTabSize - 1)];
+#ifdef __CUDA_ARCH__
+    const double2 tt = __ldg((const double2*)&kDevLogTab[(hi >> 13) & (kLogTabSize - 1)]);
+    LogTabEntry t;
+    t.c = tt.x; t.neg_log_c = tt.y;
+#else
+    const LogTabEntry t = kHostLogTab[(hi >> 13) & (kLogTabSize - 1)];
+#endif
     const double r = fma(m, t.c, -1.0);
     const double e = (double)ex;
 #ifdef __CUDA_ARCH__
@@ -118,6 +125,27 @@ H3D_HD double fast_log_pos(double x, const LogTabEntry* tab) {
     const double tail = fma(r * r, p, e * 2.319046813846299616e-17);      // + e ln2_lo
     return fma(e, 0.693147180559945286, t.neg_log_c) + (r + tail);
 #endif
+}
+
+// Natural logarithm as used by the special-function code below: absolute error
+// <= ~1.5e-16 max(1, |ln x|) (what log-probabilities and (a - .5) ln a terms
+// need; NOT a relative-accuracy log near x = 1), table-driven for normal
+// positive arguments, the library routine otherwise (zero, subnormal, inf, NaN,
+// negative).  One out-of-line copy per kernel (instruction-cache footprint).
+H3D_HDN double m_log(double x) {
+#ifdef __CUDA_ARCH__
+    const unsigned hi = (unsigned)__double2hiint(x);
+#else
+    long long b;
+    memcpy(&b, &x, 8);
+    const unsigned hi = (unsigned)(b >> 32);
+#endif
+#ifndef H3D_MLOG_LIB
+    if (hi - 0x00100000u < 0x7fe00000u) return fast_log_pos(x);   // normal and positive
+#else
+    (void)hi;
+#endif
+    return log(x);
 }
 
 // reciprocal of a positive normal number to ~1 ulp (not correctly rounded):
@@ -533,7 +561,7 @@ H3D_HD double stirling_corr(double x) {
 // Stirling's series term of one log-gamma argument x >= 10 without the
 // "- x + .5 ln 2pi" part (which cancels or is constant in the conditional
 // likelihood): (x - .5) ln x + corr(x), table-driven log, refined-seed reciprocal
-H3D_HD double stirling_core(double x, const LogTabEntry* tab) {
+H3D_HD double stirling_core(double x) {
     const double ix = fast_rcp_pos(x);
     const double ix2 = ix * ix;
 #ifdef __CUDA_ARCH__
@@ -549,7 +577,7 @@ H3D_HD double stirling_core(double x, const LogTabEntry* tab) {
         ix2 * (-1.0 / 1680.0 + ix2 * (1.0 / 1188.0 + ix2 * (-691.0 / 360360.0 +
         ix2 * (1.0 / 156.0)))))));
 #endif
-    return fma(x - 0.5, fast_log_pos(x, tab), corr);
+    return fma(x - 0.5, fast_log_pos(x), corr);
 }
 
 // the same for arguments that may be below 10: ALL arguments of a likelihood
@@ -560,10 +588,10 @@ H3D_HD double stirling_core(double x, const LogTabEntry* tab) {
 // predication) and makes the "- n" terms a per-evaluation constant.  The
 // product is >= r (r+1) ... (r+n-1) >= 3.7e3 for r >= 0.0101 (delta <= 100/101),
 // i.e. far from 1, where the table logarithm is accurate.
-H3D_HD double stirling_core_shifted(double x, int n, const LogTabEntry* tab) {
+H3D_HD double stirling_core_shifted(double x, int n) {
     double p = x, xs = x + 1.0;
     for (int k = 1; k < n; ++k) { p *= xs; xs += 1.0; }
-    return stirling_core(xs, tab) - fast_log_pos(p, tab);
+    return stirling_core(xs) - fast_log_pos(p);
 }
 
 H3D_HD double lgamma_pos(double x) {

@@ -15,6 +15,7 @@ import time
 ENABLED = os.environ.get('H3D_TRACE', '0') not in ('', '0')
 TIMES = collections.OrderedDict()
 COUNTS = collections.Counter()
+CALLS = collections.OrderedDict()      # name -> list of per-call ms
 
 
 @contextlib.contextmanager
@@ -29,13 +30,16 @@ def stage(name):
         yield
     finally:
         torch.cuda.synchronize()
-        TIMES[name] = TIMES.get(name, 0.0) + time.perf_counter() - t0
+        dt = time.perf_counter() - t0
+        TIMES[name] = TIMES.get(name, 0.0) + dt
         COUNTS[name] += 1
+        CALLS.setdefault(name, []).append(round(1e3 * dt, 2))
 
 
 def reset():
     TIMES.clear()
     COUNTS.clear()
+    CALLS.clear()
 
 
 def report(header='', divide_by=1, file=None):
@@ -46,5 +50,8 @@ def report(header='', divide_by=1, file=None):
     print('[h3d trace] %s (top-level total %.1f ms)'
           % (header, 1e3 * tot / divide_by), file=file)
     for k, v in TIMES.items():
-        print('[h3d trace]   %-28s %9.2f ms  (%d calls)'
-              % (k, 1e3 * v / divide_by, COUNTS[k] // divide_by), file=file)
+        calls = CALLS.get(k, [])
+        spread = '' if len(calls) < 2 else '  per call: %s' % calls[:12]
+        print('[h3d trace]   %-28s %9.2f ms  (%d calls)%s'
+              % (k, 1e3 * v / divide_by, COUNTS[k] // divide_by, spread),
+              file=file)

@@ -33,20 +33,16 @@ void hc_lgamma_pos(const double* x, int n, double* out) {
     for (int i = 0; i < n; ++i) out[i] = h3d::lgamma_pos(x[i]);
 }
 void hc_fast_log(const double* x, int n, double* out) {
-    h3d::LogTabEntry tab[h3d::kLogTabSize];
-    for (int j = 0; j < h3d::kLogTabSize; ++j) h3d::log_table_entry(j, &tab[j]);
-    for (int i = 0; i < n; ++i) out[i] = h3d::fast_log_pos(x[i], tab);
+    for (int i = 0; i < n; ++i) out[i] = h3d::m_log(x[i]);
 }
 // lgamma through the likelihood's Stirling core (shifted): core - x + .5 ln 2pi
 void hc_lgamma_core(const double* x, int n, double* out) {
-    h3d::LogTabEntry tab[h3d::kLogTabSize];
-    for (int j = 0; j < h3d::kLogTabSize; ++j) h3d::log_table_entry(j, &tab[j]);
     for (int i = 0; i < n; ++i) {
         // the kernel shifts by ceil(10 - r) with r <= x the smallest argument of
         // the evaluation; here: the smallest shift that brings x itself to >= 10
         const int sh = (x[i] < 10.0) ? (int)ceil(10.0 - x[i]) : 0;
-        const double c = (sh > 0) ? h3d::stirling_core_shifted(x[i], sh, tab)
-                                  : h3d::stirling_core(x[i], tab);
+        const double c = (sh > 0) ? h3d::stirling_core_shifted(x[i], sh)
+                                  : h3d::stirling_core(x[i]);
         out[i] = (c - (double)sh) - x[i] + 0.9189385332046727;
     }
 }

@@ -143,6 +143,20 @@ def test_table_log_and_stirling_core(L):
     ref = np.log(x)
     ulp = np.abs(out - ref) / np.spacing(ref)
     assert ulp.max() <= 2.0, ulp.max()
+    # the general-purpose entry (m_log): absolute accuracy over the whole
+    # positive range, including arguments next to 1, subnormals, zero and inf
+    xg = np.concatenate([10 ** rng.uniform(-300, 300, 200000),
+                         1 + rng.normal(0, 1e-3, 100000),
+                         np.exp(rng.normal(0, 0.3, 100000)),
+                         [5e-324, 1e-310, 2.2250738585072014e-308, 0.0, np.inf]])
+    og = np.zeros(len(xg))
+    L.hc_fast_log(P(xg), len(xg), P(og))
+    with np.errstate(divide='ignore'):
+        rg = np.log(xg)
+    fin = np.isfinite(rg)
+    assert np.array_equal(og[~fin], rg[~fin])
+    assert (np.abs(og[fin] - rg[fin]) /
+            np.maximum(1.0, np.abs(rg[fin]))).max() < 2.5e-16
     xs = np.concatenate([10 ** rng.uniform(-2, 1, 200000),
                          10 ** rng.uniform(1, 6, 200000)])
     out = np.zeros(len(xs))
