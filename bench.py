@@ -322,6 +322,13 @@ def main():
     n_px_local = sum(int(s['row'].numel()) for s in out[0])
     n_d_local = sum(int(s['disp_index'].numel()) for s in out[0])
     del out
+    # a full (generation 2) collection walks every container object of the
+    # process (~1e6 with torch / scipy / pandas imported) and lands inside one
+    # timed step out of ~6 as a 70-150 ms stall: collect now and move what is
+    # alive to the permanent generation
+    import gc
+    gc.collect()
+    gc.freeze()
     sampler = ClockSampler(local_rank)
     sampler.start()
     lib().query('h3d_reset_launch_count')

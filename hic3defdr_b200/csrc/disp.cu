@@ -32,7 +32,7 @@ constexpr double kBrentXatol = 1e-5;
 constexpr int kBrentMaxfun = 500;
 constexpr double kDeltaLo = 1e-4, kDeltaHi = 100.0 / 101.0;   // dispersion.py:77
 
-enum : int { ST_EMPTY = 0, ST_NEED_EQ = 1, ST_IN_BRENT = 2, ST_DONE = 3, ST_FAILED = 4 };
+enum : int { ST_EMPTY = 0, ST_NEED_EQ = 1, ST_IN_BRENT = 2, ST_DONE = 3, ST_FAILED = 4, ST_DONE_CAPPED = 5 };
 
 struct CondReps {
     int rep[H3D_MAX_CONDS][H3D_MAX_REPS];   // replicate indices of each condition
@@ -373,8 +373,11 @@ __global__ void step_kernel(Problem* __restrict__ prob, const int* __restrict__ 
     if (estimator == H3D_EST_CML) { q.disp = nd; q.status = ST_DONE; return; }
     const double dl = fabs(q.disp - nd);                    // dispersion.py:36-42
     q.disp = nd;
-    if (dl > kQcmlTol) { q.status = ST_NEED_EQ; atomicAdd(&cnt->n_need_eq, 1); }
-    else q.status = ST_DONE;
+    if (dl > kQcmlTol && q.outer_iters < H3D_QCML_MAX_OUTER) {
+        q.status = ST_NEED_EQ; atomicAdd(&cnt->n_need_eq, 1);
+    } else {
+        q.status = (dl > kQcmlTol) ? ST_DONE_CAPPED : ST_DONE;     // see include/h3d.h
+    }
 }
 
 __global__ void reset_counters_kernel(Counters* cnt) { cnt->n_need_eq = 0; cnt->n_in_brent = 0; }
@@ -390,8 +393,8 @@ __global__ void publish_words_kernel(const unsigned long long* __restrict__ src,
 __global__ void collect_kernel(const Problem* __restrict__ prob, int n, double* __restrict__ disp_out,
                                long long* __restrict__ stats) {
     // single block
-    __shared__ long long it_sum, fev_sum, eq_sum;
-    if (threadIdx.x == 0) { it_sum = 0; fev_sum = 0; eq_sum = 0; }
+    __shared__ long long it_sum, fev_sum, eq_sum, cap_sum;
+    if (threadIdx.x == 0) { it_sum = 0; fev_sum = 0; eq_sum = 0; cap_sum = 0; }
     __syncthreads();
     for (int p = threadIdx.x; p < n; p += blockDim.x) {
         disp_out[p] = prob[p].disp;
@@ -399,9 +402,10 @@ __global__ void collect_kernel(const Problem* __restrict__ prob, int n, double* 
         atomicAdd((unsigned long long*)&fev_sum, (unsigned long long)prob[p].nfev_total);
         atomicAdd((unsigned long long*)&eq_sum,
                   (unsigned long long)((long long)prob[p].outer_iters * prob[p].n_px));
+        if (prob[p].status == ST_DONE_CAPPED) atomicAdd((unsigned long long*)&cap_sum, 1ull);
     }
     __syncthreads();
-    if (threadIdx.x == 0) { stats[0] = it_sum; stats[1] = fev_sum; stats[2] = eq_sum; }
+    if (threadIdx.x == 0) { stats[0] = it_sum; stats[1] = fev_sum; stats[2] = eq_sum; stats[3] = cap_sum; }
 }
 
 }  // namespace h3d
@@ -471,7 +475,7 @@ extern "C" int h3d_estimate_dispersion(const double* x, const double* f, long lo
     H3D_REQUIRE(seg_start_host[0] == 0 && n_px <= ld, "segments must start at 0 and fit in ld");
     const int n_prob = n_seg * n_conds;
     for (int p = 0; p < n_prob; ++p) disp_per_dist_host[p] = NAN;
-    if (stats_host) for (int k = 0; k < 8; ++k) stats_host[k] = 0;
+    if (stats_host) for (int k = 0; k < 9; ++k) stats_host[k] = 0;
     if (n_px == 0) return H3D_OK;
 
     // chunk tables (host)
@@ -617,17 +621,18 @@ extern "C" int h3d_estimate_dispersion(const double* x, const double* f, long lo
                                             (volatile unsigned long long*)((char*)pin_dev + 256), n_prob);
     H3D_LAUNCHED("publish_words_kernel");
     publish_words_kernel<<<1, 32, 0, st>>>((const unsigned long long*)stats_dev,
-                                           (volatile unsigned long long*)((char*)pin_dev + 64), 3);
+                                           (volatile unsigned long long*)((char*)pin_dev + 64), 4);
     H3D_LAUNCHED("publish_words_kernel");
     H3D_CHECK(cudaStreamSynchronize(st));
     memcpy(disp_per_dist_host, (char*)pin_host + 256, (size_t)n_prob * 8);
     long long h_stats[4] = {0, 0, 0, 0};
-    memcpy(h_stats, (char*)pin_host + 64, 3 * sizeof(long long));
+    memcpy(h_stats, (char*)pin_host + 64, 4 * sizeof(long long));
     if (stats_host) {
         stats_host[0] = h_stats[0]; stats_host[1] = h_stats[1]; stats_host[2] = h_stats[2];
         stats_host[3] = (long long)(h3d_launch_count() - launches_before);
         stats_host[4] = eq_launches; stats_host[5] = (long long)eq_us;
         stats_host[6] = nll_launches; stats_host[7] = (long long)nll_us;
+        stats_host[8] = h_stats[3];
     }
     return H3D_OK;
 }

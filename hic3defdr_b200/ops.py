@@ -314,7 +314,7 @@ def estimate_dispersion(x_soa, f_soa, seg_start, design, estimator='qcml'):
     n_seg = len(seg) - 1
     ld = x_soa.shape[1]
     out = np.empty((n_seg, n_conds))
-    stats = np.zeros(8, dtype=np.int64)
+    stats = np.zeros(9, dtype=np.int64)
     wsb = lib().query('h3d_estimate_dispersion_ws_bytes', int(seg[-1]), n_seg,
                       n_reps, n_conds)
     ws = workspace(wsb)
@@ -323,13 +323,21 @@ def estimate_dispersion(x_soa, f_soa, seg_start, design, estimator='qcml'):
                ptr(seg), n_seg, ptr(db), n_reps, n_conds,
                ESTIMATORS[estimator], ptr(out), ptr(stats), ptr(ws), wsb,
                _stream())
+    if stats[8]:
+        import sys
+        print('  warning: the qCML fixed point of %d (distance, condition) bins '
+              'did not settle within its tolerance (tiny bins with a large '
+              'dispersion; the reference loops forever there, '
+              'hic3defdr/util/dispersion.py:36-42); their last iterate is used'
+              % int(stats[8]), file=sys.stderr)
     return out, dict(outer_iterations=int(stats[0]),
                      nll_evaluations=int(stats[1]),
                      pixel_equalizations=int(stats[2]),
                      launches=int(stats[3]),
                      equalize_launches=int(stats[4]),
                      equalize_us=int(stats[5]),
-                     nll_launches=int(stats[6]), nll_us=int(stats[7]))
+                     nll_launches=int(stats[6]), nll_us=int(stats[7]),
+                     capped_segments=int(stats[8]))
 
 
 def _single_bin(data, f, estimator):

@@ -157,9 +157,17 @@ size_t h3d_stable_rank_ws_bytes(long long n, int n_keys);
  * (util/scaled_nb.py:186-275).  x, f: SoA (n_reps, ld) pooled by distance
  * (segment d = [seg_start_host[d], seg_start_host[d + 1])).
  * disp_per_dist_host: (n_seg, n_conds) HOST output, NaN for empty segments.
- * stats_host (may be NULL): 8 int64 = {outer iterations, NLL evaluations,
+ * stats_host (may be NULL): 9 int64 = {outer iterations, NLL evaluations,
  * pixel-equalisations, kernel launches, equalize launches, equalize time (us,
- * CUDA events on ``stream``), NLL launches, NLL time (us)}.  Synchronises. */
+ * CUDA events on ``stream``), NLL launches, NLL time (us), segments stopped at
+ * the outer-iteration cap}.  Synchronises.
+ * The qCML fixed point ``while |disp - new| > 1e-4`` has no iteration cap in
+ * the reference (util/dispersion.py:36-42: ``it`` is never incremented) and
+ * cycles forever where the dispersion is large and the bin small (the bounded
+ * Brent search resolves delta to 1e-5, i.e. disp = delta / (1 - delta) only
+ * to ~0.05 at disp ~ 66).  Here a segment stops after H3D_QCML_MAX_OUTER
+ * outer iterations with its last iterate, and is counted in stats[8]. */
+#define H3D_QCML_MAX_OUTER 100
 #define H3D_EST_QCML 0
 #define H3D_EST_CML 1
 #define H3D_EST_MME 2
