@@ -19,17 +19,22 @@ from hic3defdr_b200.trace import stage
 from hic3defdr_b200.trend import lowess_fit, weighted_lowess_fit
 
 
-def prepare_chrom(csr, bias_raw, design, dist_min=4, dist_max=200,
-                  bias_thresh=0.1, mean_thresh=1.0, norm='conditional_mor',
-                  n_bins=-1, loop_pixels=None):
-    """hic3defdr/analysis/analysis.py:63-133 for one chromosome.
-    ``csr``: ops.DeviceCSR; ``bias_raw``: (n_bins, R) unfiltered bias."""
+def prepare_chrom_steps(csr, bias_raw, design, dist_min=4, dist_max=200,
+                        bias_thresh=0.1, mean_thresh=1.0,
+                        norm='conditional_mor', n_bins=-1, loop_pixels=None):
+    """hic3defdr/analysis/analysis.py:63-133 for one chromosome as a generator:
+    it yields an ``ops.Readback`` wherever the host needs a count from the
+    device (number of union pixels, number of tested pixels) and is resumed
+    with the value, so that a driver can keep several chromosomes in flight on
+    separate streams (``prepare_many``).  Returns the chromosome state."""
     if n_bins == -1:
         n_bins = int(dist_max / 5)
     bias = ops.filter_bias(bias_raw, bias_thresh)
-    u = ops.union_gather(csr, dist_max, bias)
+    offs, pending = ops.union_count_async(csr, dist_max, bias)
+    n_px = int((yield pending)[0])
+    u = ops.union_emit(csr, dist_max, bias, offs, n_px)
     st = dict(bias=bias, row=u['row'], col=u['col'], raw=u['raw'])
-    if u['row'].numel() == 0:
+    if n_px == 0:
         r = csr.n_reps
         st.update(size_factors=torch.empty((0, r), dtype=torch.float64,
                                            device='cuda'),
@@ -42,12 +47,80 @@ def prepare_chrom(csr, bias_raw, design, dist_min=4, dist_max=200,
     scaled, sf, disp_idx = ops.scale_filter(
         u['row'], u['col'], u['balanced'], table, design, dist_max,
         mean_thresh, dist_min)
+    index, pending = ops.mask_to_index_async(disp_idx)
+    n_d = int((yield pending)[0])
     st.update(size_factors=sf, scaled=scaled, disp_idx=disp_idx,
-              disp_index=ops.mask_to_index(disp_idx))
+              disp_index=index[:n_d])
     if loop_pixels is not None:
         st['loop_idx'] = ops.loop_membership(st['row'], st['col'],
                                              st['disp_index'], loop_pixels)
     return st
+
+
+def prepare_chrom(csr, bias_raw, design, *args, **kw):
+    """One chromosome, synchronously (same arguments as
+    ``prepare_chrom_steps``)."""
+    gen = prepare_chrom_steps(csr, bias_raw, design, *args, **kw)
+    try:
+        pending = next(gen)
+        while True:
+            pending = gen.send(pending.get())
+    except StopIteration as stop:
+        return stop.value
+
+
+_PREPARE_STREAMS = {}
+
+
+def prepare_many(chrom_inputs, design, n_streams=4, sink=None, **kw):
+    """``prepare_chrom`` over an iterable of (csr, bias_raw), up to
+    ``n_streams`` chromosomes in flight, one CUDA stream each: a chromosome is
+    ~25 short kernels, several of them latency-bound (rank scan, median
+    select), and two host read-backs; interleaving hides both.  Results are
+    identical to the sequential loop (each chromosome's kernels keep their
+    order on their own stream).  ``sink(i, name, tensor)`` as in
+    ``run_to_qvalues``."""
+    main = torch.cuda.current_stream()
+    dev_i = torch.cuda.current_device()
+    streams = _PREPARE_STREAMS.setdefault(dev_i, [])
+    while len(streams) < n_streams:
+        streams.append(torch.cuda.Stream())
+    states = {}
+    active = []          # [index, stream, generator, pending Readback]
+
+    def finish(i, stream, st):
+        states[i] = st
+        if sink is not None:
+            with torch.cuda.stream(stream):
+                for k in PREPARE_OUTPUTS:
+                    sink(i, k, st[k])
+
+    def advance():
+        i, stream, gen, pending = active.pop(0)
+        with torch.cuda.stream(stream):
+            try:
+                active.append([i, stream, gen, gen.send(pending.get())])
+            except StopIteration as stop:
+                finish(i, stream, stop.value)
+
+    for i, (csr, b) in enumerate(chrom_inputs):
+        # chromosome i always runs on stream i mod n_streams: the caching
+        # allocator then sees the same request sequence per stream every run
+        stream = streams[i % n_streams]
+        while any(a[1] is stream for a in active):
+            advance()
+        stream.wait_stream(main)              # inputs were made ready on main
+        gen = prepare_chrom_steps(csr, b, design, **kw)
+        with torch.cuda.stream(stream):
+            try:
+                active.append([i, stream, gen, next(gen)])
+            except StopIteration as stop:
+                finish(i, stream, stop.value)
+    while active:
+        advance()
+    for s in streams:
+        main.wait_stream(s)
+    return [states[i] for i in sorted(states)]
 
 
 def pool_by_distance(states, dist_max):
@@ -219,14 +292,11 @@ def run_to_qvalues(chrom_inputs, design, dist_min=4, dist_max=200,
     Returns (states, disp_per_dist, trend callables, qcml stats)."""
     design = np.asarray(design).astype(bool)
     emit = sink if sink is not None else (lambda i, name, t: None)
-    states = []
     with stage('prepare_data'):
-        for i, (csr, b) in enumerate(chrom_inputs):
-            st = prepare_chrom(csr, b, design, dist_min, dist_max, bias_thresh,
-                               mean_thresh, norm, n_bins)
-            for k in PREPARE_OUTPUTS:
-                emit(i, k, st[k])
-            states.append(st)
+        states = prepare_many(chrom_inputs, design, sink=sink,
+                              dist_min=dist_min, dist_max=dist_max,
+                              bias_thresh=bias_thresh, mean_thresh=mean_thresh,
+                              norm=norm, n_bins=n_bins)
     with stage('estimate_disp'):
         dpd, fns, stats = estimate_disp(states, design, dist_max,
                                         estimator=estimator, frac=frac,

@@ -72,6 +72,42 @@ def to_host(t):
     return box[:nbytes].view(t.dtype).numpy().reshape(tuple(t.shape)).copy()
 
 
+class Readback(object):
+    """Deferred ``to_host``: the publish kernel is enqueued on the current
+    stream now, ``get()`` synchronises THAT stream later and returns the numpy
+    copy.  Lets several chromosomes (one stream each) keep their kernels
+    queued while the host waits for one of them."""
+    _box = {}
+    _next = {}
+    SLOT = 64          # bytes per slot
+    N_SLOTS = 1024
+
+    def __init__(self, t):
+        import threading
+        t = t.contiguous()
+        self.dtype, self.shape = t.dtype, tuple(t.shape)
+        self.nbytes = t.numel() * t.element_size()
+        assert self.nbytes % 8 == 0 and 0 < self.nbytes <= self.SLOT
+        key = (torch.cuda.current_device(), threading.get_ident())
+        if key not in self._box:
+            self._box[key] = torch.zeros(self.SLOT * self.N_SLOTS,
+                                         dtype=torch.uint8).pin_memory()
+            self._next[key] = 0
+        slot = self._next[key]
+        self._next[key] = (slot + 1) % self.N_SLOTS
+        self.view = self._box[key][slot * self.SLOT:
+                                   slot * self.SLOT + self.nbytes]
+        self.stream = torch.cuda.current_stream()
+        self.keep = t
+        lib().call('h3d_publish', ptr(t), ptr(self.view), self.nbytes,
+                   self.stream.cuda_stream)
+
+    def get(self):
+        self.stream.synchronize()
+        self.keep = None
+        return self.view.view(self.dtype).numpy().reshape(self.shape).copy()
+
+
 def _check_failed(counter, what):
     n = int(to_host(counter.to(torch.int64))[0])
     if n:
@@ -152,7 +188,30 @@ def union_gather(csr, dist_thresh, bias=None):
     lib().call('h3d_union_count', csr.n_reps, ip, csr.is64, ix, dt,
                _DTYPES[csr.dtype], bptr, n, int(dist_thresh), ptr(offs),
                ptr(ws), wsb, _stream())
-    n_px = int(to_host(offs[n:n + 1].to(torch.int64))[0])
+    n_px = int(Readback(offs[n:n + 1].to(torch.int64)).get()[0])
+    return union_emit(csr, dist_thresh, bias, offs, n_px)
+
+
+def union_count_async(csr, dist_thresh, bias=None):
+    """First half of ``union_gather``: per-row pixel counts / offsets on the
+    device and a ``Readback`` of the total; finish with ``union_emit``."""
+    n = csr.n_bins
+    ip, ix, dt = csr.pointer_arrays()
+    offs = torch.empty(n + 1, dtype=torch.int32, device='cuda')
+    wsb = lib().query('h3d_union_ws_bytes', n)
+    ws = workspace(wsb)
+    bptr = ptr(bias) if bias is not None else None
+    lib().call('h3d_union_count', csr.n_reps, ip, csr.is64, ix, dt,
+               _DTYPES[csr.dtype], bptr, n, int(dist_thresh), ptr(offs),
+               ptr(ws), wsb, _stream())
+    return offs, Readback(offs[n:n + 1].to(torch.int64))
+
+
+def union_emit(csr, dist_thresh, bias, offs, n_px):
+    """Second half of ``union_gather`` given the row offsets and the total."""
+    n = csr.n_bins
+    ip, ix, dt = csr.pointer_arrays()
+    bptr = ptr(bias) if bias is not None else None
     row = torch.empty(n_px, dtype=torch.int32, device='cuda')
     col = torch.empty_like(row)
     dist = torch.empty_like(row)
@@ -273,6 +332,20 @@ def mask_to_index(mask):
     lib().call('h3d_mask_to_index', ptr(m), n, ptr(idx), ptr(cnt), ptr(ws),
                wsb, _stream())
     return idx[:int(to_host(cnt)[0])]
+
+
+def mask_to_index_async(mask):
+    """``mask_to_index`` without the host wait: (index buffer of full length,
+    Readback of the number of set entries)."""
+    m = dev(mask, torch.uint8)
+    n = m.numel()
+    idx = torch.empty(n, dtype=torch.int32, device='cuda')
+    cnt = torch.zeros(1, dtype=torch.int64, device='cuda')
+    wsb = lib().query('h3d_mask_to_index_ws_bytes', n)
+    ws = workspace(wsb)
+    lib().call('h3d_mask_to_index', ptr(m), n, ptr(idx), ptr(cnt), ptr(ws),
+               wsb, _stream())
+    return idx, Readback(cnt)
 
 
 def loop_membership(row, col, index, pixels):
