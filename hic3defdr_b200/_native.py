@@ -29,6 +29,14 @@ SIGNATURES = {
     'h3d_size_factors': (c_int, [vp, vp, c_ll, c_int, c_int, c_int, c_int, vp,
                                  vp, c_sz, vp]),
     'h3d_size_factors_ws_bytes': (c_sz, [c_ll, c_int, c_int]),
+    'h3d_sf_num_groups': (c_int, [c_int, c_int, c_int]),
+    'h3d_sf_group_bounds': (c_int, [c_ll, c_int, c_int, c_int, vp, vp, vp]),
+    'h3d_sf_values': (c_int, [vp, vp, c_ll, c_int, c_int, vp, vp]),
+    'h3d_sf_group_reduce': (c_int, [vp, c_ll, vp, c_int, c_int, c_int, vp, vp,
+                                    vp]),
+    'h3d_sf_table': (c_int, [vp, vp, vp, c_int, c_int, c_int, c_int, c_int,
+                             vp, vp, c_sz, vp]),
+    'h3d_sf_table_ws_bytes': (c_sz, [c_int, c_int]),
     'h3d_scale_filter': (c_int, [vp, vp, vp, vp, c_int, vp, c_ll, c_int, c_int,
                                  c_int, c_dbl, c_int, vp, vp, vp]),
     'h3d_mask_to_index': (c_int, [vp, c_ll, vp, vp, vp, c_sz, vp]),

@@ -16,7 +16,10 @@ Differences a caller can observe (all documented in DESIGN.md):
     the next step of ``run_to_qvalues`` does not re-read them from disk; every
     step still works from the files alone in a fresh process;
   * with ``torch.distributed`` initialised (one process per GPU), chromosomes
-    are sharded across ranks (hic3defdr_b200/dist.py).
+    are sharded across ranks (hic3defdr_b200/dist.py); with fewer chromosomes
+    than ranks (or ``H3D_SHARD=rows``) every chromosome is sharded by row
+    range instead and the ranks write their slices of the same ``.npy`` files
+    (outdir must be on a file system all ranks share, as on one node).
 """
 import json
 import os
@@ -30,7 +33,7 @@ import scipy.sparse as sparse
 import torch
 
 from hic3defdr_b200 import dist as hdist
-from hic3defdr_b200 import engine, ops
+from hic3defdr_b200 import engine, ops, staging
 
 
 def eprint(*args, **kwargs):
@@ -89,6 +92,7 @@ class HiC3DeFDR(object):
                 pickle.dump(state, handle, -1)
         hdist.barrier()
         self._cache = {}
+        self._shards = {}
         self.timings = {}
 
     # ---------------------------------------------------------------- core
@@ -210,8 +214,65 @@ class HiC3DeFDR(object):
             return pickle.dump(disp_fn, h, -1)
 
     # ------------------------------------------------------------ helpers
+    def _row_sharded(self):
+        """True when every rank works on a row range of every chromosome
+        (BASELINE config 4) rather than on whole
+        chromosomes: ``H3D_SHARD=rows``, or by default when there are fewer
+        chromosomes than ranks (``H3D_SHARD=chroms`` forces the other way)."""
+        ws = hdist.world_size()
+        if ws == 1:
+            return False
+        mode = os.environ.get('H3D_SHARD', 'auto')
+        if mode not in ('auto', 'rows', 'chroms'):
+            raise ValueError('H3D_SHARD must be auto, rows or chroms')
+        return mode == 'rows' or (mode == 'auto' and len(self.chroms) < ws)
+
     def _my_chroms(self):
+        if self._row_sharded():
+            return list(self.chroms)
         return hdist.shard_chroms(self.chroms, self._chrom_weight)
+
+    def _shard_bounds(self, chrom):
+        """(lo, hi, dlo, dhi): this rank's slice of the union-aligned and of
+        the disp_idx-aligned arrays of a row-sharded chromosome.  Known from
+        ``prepare_data`` in the same process; in a fresh process the pixels are
+        cut evenly (the later steps accept any contiguous partition)."""
+        b = self._shards.get(chrom)
+        if b is None:
+            ws, me = hdist.world_size(), hdist.rank()
+            disp_idx = np.load('%s/disp_idx_%s.npy' % (self.outdir, chrom),
+                               mmap_mode='r')
+            n = disp_idx.shape[0]
+            lo, hi = n * me // ws, n * (me + 1) // ws
+            dlo = int(np.count_nonzero(disp_idx[:lo]))
+            b = (lo, hi, dlo, dlo + int(np.count_nonzero(disp_idx[lo:hi])))
+            self._shards[chrom] = b
+        return b
+
+    def _save_sharded(self, items):
+        """items: list of (tensor, name, chrom), each this rank's slice (rank
+        order = array order) of one output array: rank 0 creates the ``.npy``
+        at its full size, every rank writes its rows in place."""
+        ws, me = hdist.world_size(), hdist.rank()
+        host = [(d.cpu().numpy() if isinstance(d, torch.Tensor) else
+                 np.asarray(d)) for d, _, _ in items]
+        lens = hdist._all_gather_counts(
+            np.array([h.shape[0] for h in host], dtype=np.int64))  # (ws, items)
+        paths = ['%s/%s_%s.npy' % (self.outdir, n, c) for _, n, c in items]
+        if me == 0:
+            for h, p, tot in zip(host, paths, lens.sum(axis=0)):
+                m = np.lib.format.open_memmap(
+                    p, mode='w+', dtype=h.dtype, shape=(int(tot),) + h.shape[1:])
+                del m
+        hdist.barrier()
+        for k, (h, p) in enumerate(zip(host, paths)):
+            if h.shape[0]:
+                m = np.load(p, mmap_mode='r+')
+                a = int(lens[:me, k].sum())
+                m[a:a + h.shape[0]] = h
+                m.flush()
+                del m
+        hdist.barrier()
 
     def _chrom_weight(self, chrom):
         try:
@@ -245,6 +306,19 @@ class HiC3DeFDR(object):
             elif name == 'disp_index':
                 di = self._chrom_state(chrom, ['disp_idx'])['disp_idx']
                 c['disp_index'] = ops.mask_to_index(di)
+            elif self._row_sharded():
+                lo, hi, dlo, dhi = self._shard_bounds(chrom)
+                arr = np.load('%s/%s_%s.npy' % (self.outdir, name, chrom),
+                              mmap_mode='r')
+                if name in ('row', 'col', 'raw', 'scaled', 'disp_idx') or \
+                        (name == 'size_factors' and arr.ndim == 2):
+                    arr = arr[lo:hi]
+                elif name != 'size_factors':
+                    arr = arr[dlo:dhi]
+                arr = np.ascontiguousarray(arr)
+                if arr.dtype == np.bool_:
+                    arr = arr.view(np.uint8)
+                c[name] = ops.dev(arr)
             else:
                 arr = self.load_data(name, chrom)
                 if arr.dtype == np.bool_:
@@ -281,6 +355,12 @@ class HiC3DeFDR(object):
             mats = list(ex.map(
                 lambda p: sparse.load_npz(p.replace('<chrom>', chrom)).tocsr(),
                 self.raw_npz_patterns))
+        sharded = self._row_sharded()
+        if sharded:
+            bounds = hdist.row_ranges(staging.row_weights(mats))
+            me = hdist.rank()
+            mats = staging.shard_rows(mats, int(bounds[me]),
+                                      int(bounds[me + 1]))
         csr = ops.DeviceCSR(mats)
         del mats
         loop_pixels = None
@@ -293,7 +373,9 @@ class HiC3DeFDR(object):
         eprint('  loading balanced data', skip=not verbose)
         eprint('  computing size factors', skip=not verbose)
         eprint('  computing disp_idx', skip=not verbose)
-        st = engine.prepare_chrom(
+        prepare = engine.prepare_chrom_sharded if sharded else \
+            engine.prepare_chrom
+        st = prepare(
             csr, bias_raw, self._design(), self.dist_thresh_min,
             self.dist_thresh_max, self.bias_thresh, self.mean_thresh, norm,
             n_bins, loop_pixels)
@@ -303,7 +385,21 @@ class HiC3DeFDR(object):
                     k, chrom)
                    for k in ('loop_idx', 'row', 'col', 'raw', 'size_factors',
                              'scaled', 'disp_idx') if k in st]
-        self._save_many(to_save, n_threads)
+        if sharded:
+            whole = [t for t in to_save
+                     if t[1] == 'size_factors' and t[0].dim() == 1]
+            to_save = [t for t in to_save if t not in whole]
+            if whole and hdist.rank() == 0:      # (R,) factors: same everywhere
+                self._save_many(whole, n_threads)
+            counts = hdist._all_gather_counts(np.array(
+                [st['row'].numel(), st['disp_index'].numel()]))
+            me = hdist.rank()
+            lo, dlo = [int(v) for v in counts[:me].sum(axis=0)]
+            self._shards[chrom] = (lo, lo + int(counts[me, 0]),
+                                   dlo, dlo + int(counts[me, 1]))
+            self._save_sharded(to_save)
+        else:
+            self._save_many(to_save, n_threads)
         st.pop('scaled')
         self._cache[chrom] = st
 
@@ -332,8 +428,9 @@ class HiC3DeFDR(object):
             for cond, fn in zip(self.design.columns, fns):
                 self.save_disp_fn(cond, fn)
             self.save_data(disp_per_dist, 'disp_per_dist')
-        self._save_many([(s['disp'], 'disp', c)
-                         for c, s in zip(mine, states)], n_threads)
+        save = self._save_sharded if self._row_sharded() else \
+            (lambda items: self._save_many(items, n_threads))
+        save([(s['disp'], 'disp', c) for c, s in zip(mine, states)])
         hdist.barrier()
 
     # ---------------------------------------------------------------- lrt
@@ -353,9 +450,10 @@ class HiC3DeFDR(object):
         eprint('  computing LRT results', skip=not verbose)
         engine.lrt_chrom(s, self._design(), refit_mu)
         eprint('  saving results to disk', skip=not verbose)
-        self._save_many([(s[k], k, chrom) for k in
-                         ('pvalues', 'llr', 'mu_hat_null', 'mu_hat_alt')],
-                        n_threads)
+        save = self._save_sharded if self._row_sharded() else \
+            (lambda items: self._save_many(items, n_threads))
+        save([(s[k], k, chrom) for k in
+              ('pvalues', 'llr', 'mu_hat_null', 'mu_hat_alt')])
         for k in ('llr', 'mu_hat_null', 'mu_hat_alt'):
             s.pop(k)
 
@@ -367,8 +465,8 @@ class HiC3DeFDR(object):
         names = ['pvalues'] + (['loop_idx'] if self.loop_patterns else [])
         states = [self._chrom_state(c, names) for c in mine]
         engine.bh(states, use_loop_idx=bool(self.loop_patterns))
-        self._save_many([(s['qvalues'], 'qvalues', c)
-                         for c, s in zip(mine, states)])
+        save = self._save_sharded if self._row_sharded() else self._save_many
+        save([(s['qvalues'], 'qvalues', c) for c, s in zip(mine, states)])
         hdist.barrier()
 
     def run_to_qvalues(self, norm='conditional_mor', n_bins_norm=-1,

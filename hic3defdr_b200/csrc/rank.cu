@@ -454,15 +454,79 @@ extern "C" size_t h3d_size_factors_ws_bytes(long long n_px, int n_reps, int dist
            4 * ws_pad((size_t)(gmax + 1) * 8) + 3 * ws_pad((size_t)gmax * n_reps * 8) + ws_pad(64);
 }
 
+// the four stages of the size-factor computation; h3d_size_factors chains them on
+// one device, hic3defdr_b200/dist.py puts collectives between them when the pixels
+// of one chromosome are sharded over several GPUs by row range
+static int sf_group_bounds(long long n_total, int dist_max, int n_bins, int norm,
+                           const long long* key_start, long long* gstart, cudaStream_t st) {
+    const bool conditional = (norm == H3D_NORM_CONDITIONAL_MOR || norm == H3D_NORM_CONDITIONAL_SCALING);
+    if (!conditional) n_bins = 0;
+    const int n_groups = sf_groups(dist_max, n_bins, norm);
+    group_bounds_kernel<<<div_up(n_groups + 1, 128), 128, 0, st>>>(
+        n_total, n_groups, n_bins, conditional ? 1 : 0, conditional ? key_start : nullptr, gstart);
+    H3D_LAUNCHED("group_bounds_kernel");
+    return H3D_OK;
+}
+
+static int sf_values(const double* balanced, const int* rank, long long n_px, int n_reps, int norm,
+                     unsigned long long* values, cudaStream_t st) {
+    const bool want_ratio = (norm == H3D_NORM_CONDITIONAL_MOR || norm == H3D_NORM_MEDIAN_OF_RATIOS);
+    if (n_px <= 0) return H3D_OK;
+    ratio_scatter_kernel<<<div_up(n_px, 256), 256, 0, st>>>(balanced, rank, n_px, n_reps,
+                                                           want_ratio ? 1 : 0, values);
+    H3D_LAUNCHED("ratio_scatter_kernel");
+    return H3D_OK;
+}
+
+static int sf_group_reduce(const unsigned long long* values, long long ld, const long long* gstart,
+                           int n_groups, int n_reps, int norm, double* red, long long* valid,
+                           cudaStream_t st) {
+    const bool want_ratio = (norm == H3D_NORM_CONDITIONAL_MOR || norm == H3D_NORM_MEDIAN_OF_RATIOS);
+    if (n_groups <= 0) return H3D_OK;
+    dim3 grid(n_groups, n_reps);
+    if (want_ratio) {
+        const size_t smem = 2 * 8192 * sizeof(unsigned);
+        H3D_CHECK(cudaFuncSetAttribute(median_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        median_select_kernel<<<grid, 1024, smem, st>>>(values, ld, gstart, red, valid, n_reps);
+        H3D_LAUNCHED("median_select_kernel");
+    } else {
+        group_sum_kernel<<<grid, 1024, 0, st>>>(values, ld, gstart, red, n_reps);
+        H3D_LAUNCHED("group_sum_kernel");
+    }
+    return H3D_OK;
+}
+
+extern "C" size_t h3d_sf_table_ws_bytes(int n_groups, int n_reps) {
+    return ws_pad((size_t)(n_groups + 1) * 8) + ws_pad((size_t)n_groups * n_reps * 8) + ws_pad(64);
+}
+
+static int sf_table(const double* red, const long long* gstart, const long long* key_start,
+                    int n_groups, int n_reps, int dist_max, int n_bins, int norm, double* table,
+                    void* ws, size_t ws_bytes, cudaStream_t st) {
+    const bool conditional = (norm == H3D_NORM_CONDITIONAL_MOR || norm == H3D_NORM_CONDITIONAL_SCALING);
+    if (!conditional) n_bins = 0;
+    Workspace w(ws, ws_bytes);
+    double* d_b = w.take<double>(n_groups + 1);
+    double* s_b = w.take<double>((size_t)n_groups * n_reps);
+    int* n_occ = w.take<int>(1);
+    if (!d_b || !s_b || !n_occ) {
+        set_error("sf_table workspace too small");
+        return H3D_ERR_WORKSPACE;
+    }
+    sf_table_kernel<<<1, 256, 0, st>>>(red, gstart, conditional ? key_start : nullptr, n_groups, n_reps,
+                                       dist_max, n_bins, norm, d_b, s_b, n_occ, table);
+    H3D_LAUNCHED("sf_table_kernel");
+    return H3D_OK;
+}
+
 extern "C" int h3d_size_factors(const int* dist, const double* balanced, long long n_px,
-                                int n_reps, int dist_max, int n_bins, int norm, double* sf_table,
+                                int n_reps, int dist_max, int n_bins, int norm, double* sf_table_out,
                                 void* ws, size_t ws_bytes, h3d_stream_t stream) {
     H3D_REQUIRE(n_reps >= 1 && n_reps <= H3D_MAX_REPS, "n_reps out of range");
     H3D_REQUIRE(norm >= 0 && norm <= 3, "unknown norm");
     H3D_REQUIRE(n_px >= 1, "no pixels");
     cudaStream_t st = (cudaStream_t)stream;
     const bool conditional = (norm == H3D_NORM_CONDITIONAL_MOR || norm == H3D_NORM_CONDITIONAL_SCALING);
-    const bool want_ratio = (norm == H3D_NORM_CONDITIONAL_MOR || norm == H3D_NORM_MEDIAN_OF_RATIOS);
     if (!conditional) n_bins = 0;
     const int n_groups = sf_groups(dist_max, n_bins, norm);
     Workspace w(ws, ws_bytes);
@@ -474,35 +538,62 @@ extern "C" int h3d_size_factors(const int* dist, const double* balanced, long lo
     long long* gstart = w.take<long long>(n_groups + 1);
     long long* valid = w.take<long long>(n_groups + 1);
     double* red = w.take<double>((size_t)n_groups * n_reps);
-    double* d_b = w.take<double>(n_groups + 1);
-    double* s_b = w.take<double>((size_t)n_groups * n_reps);
-    int* n_occ = w.take<int>(1);
-    if (!rank_ws || !rank || !sorted || !key_start || !gstart || !valid || !red || !d_b || !s_b || !n_occ) {
+    const size_t table_ws_bytes = h3d_sf_table_ws_bytes(n_groups, n_reps);
+    void* table_ws = w.take<char>(table_ws_bytes);
+    if (!rank_ws || !rank || !sorted || !key_start || !gstart || !valid || !red || !table_ws) {
         set_error("size_factors workspace too small");
         return H3D_ERR_WORKSPACE;
     }
+    int rc;
     if (conditional) {
-        int rc = stable_rank_impl(dist, n_px, dist_max + 1, rank, key_start, rank_ws, rank_ws_bytes, st);
+        rc = stable_rank_impl(dist, n_px, dist_max + 1, rank, key_start, rank_ws, rank_ws_bytes, st);
         if (rc) return rc;
     }
-    group_bounds_kernel<<<div_up(n_groups + 1, 128), 128, 0, st>>>(
-        n_px, n_groups, n_bins, conditional ? 1 : 0, conditional ? key_start : nullptr, gstart);
-    H3D_LAUNCHED("group_bounds_kernel");
-    ratio_scatter_kernel<<<div_up(n_px, 256), 256, 0, st>>>(balanced, conditional ? rank : nullptr,
-                                                           n_px, n_reps, want_ratio ? 1 : 0, sorted);
-    H3D_LAUNCHED("ratio_scatter_kernel");
-    dim3 grid(n_groups, n_reps);
-    if (want_ratio) {
-        const size_t smem = 2 * 8192 * sizeof(unsigned);
-        H3D_CHECK(cudaFuncSetAttribute(median_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        median_select_kernel<<<grid, 1024, smem, st>>>(sorted, n_px, gstart, red, valid, n_reps);
-        H3D_LAUNCHED("median_select_kernel");
-    } else {
-        group_sum_kernel<<<grid, 1024, 0, st>>>(sorted, n_px, gstart, red, n_reps);
-        H3D_LAUNCHED("group_sum_kernel");
-    }
-    sf_table_kernel<<<1, 256, 0, st>>>(red, gstart, conditional ? key_start : nullptr, n_groups, n_reps,
-                                       dist_max, n_bins, norm, d_b, s_b, n_occ, sf_table);
-    H3D_LAUNCHED("sf_table_kernel");
-    return H3D_OK;
+    if ((rc = sf_group_bounds(n_px, dist_max, n_bins, norm, key_start, gstart, st))) return rc;
+    if ((rc = sf_values(balanced, conditional ? rank : nullptr, n_px, n_reps, norm, sorted, st))) return rc;
+    if ((rc = sf_group_reduce(sorted, n_px, gstart, n_groups, n_reps, norm, red, valid, st))) return rc;
+    return sf_table(red, gstart, key_start, n_groups, n_reps, dist_max, n_bins, norm, sf_table_out,
+                    table_ws, table_ws_bytes, st);
+}
+
+// ---- the same stages, one entry point each (row-sharded chromosomes) -------
+
+extern "C" int h3d_sf_num_groups(int dist_max, int n_bins, int norm) {
+    const bool conditional = (norm == H3D_NORM_CONDITIONAL_MOR || norm == H3D_NORM_CONDITIONAL_SCALING);
+    return sf_groups(dist_max, conditional ? n_bins : 0, norm);
+}
+
+extern "C" int h3d_sf_group_bounds(long long n_total, int dist_max, int n_bins, int norm,
+                                   const long long* key_start, long long* gstart,
+                                   h3d_stream_t stream) {
+    H3D_REQUIRE(norm >= 0 && norm <= 3, "unknown norm");
+    H3D_REQUIRE(n_total >= 1, "no pixels");
+    return sf_group_bounds(n_total, dist_max, n_bins, norm, key_start, gstart, (cudaStream_t)stream);
+}
+
+extern "C" int h3d_sf_values(const double* balanced, const int* rank, long long n_px, int n_reps,
+                             int norm, double* values, h3d_stream_t stream) {
+    H3D_REQUIRE(n_reps >= 1 && n_reps <= H3D_MAX_REPS, "n_reps out of range");
+    H3D_REQUIRE(norm >= 0 && norm <= 3, "unknown norm");
+    return sf_values(balanced, rank, n_px, n_reps, norm, (unsigned long long*)values,
+                     (cudaStream_t)stream);
+}
+
+extern "C" int h3d_sf_group_reduce(const double* values, long long ld, const long long* gstart,
+                                   int n_groups, int n_reps, int norm, double* red,
+                                   long long* valid, h3d_stream_t stream) {
+    H3D_REQUIRE(n_reps >= 1 && n_reps <= H3D_MAX_REPS, "n_reps out of range");
+    H3D_REQUIRE(norm >= 0 && norm <= 3, "unknown norm");
+    return sf_group_reduce((const unsigned long long*)values, ld, gstart, n_groups, n_reps, norm,
+                           red, valid, (cudaStream_t)stream);
+}
+
+extern "C" int h3d_sf_table(const double* red, const long long* gstart, const long long* key_start,
+                            int n_groups, int n_reps, int dist_max, int n_bins, int norm,
+                            double* sf_table_out, void* ws, size_t ws_bytes, h3d_stream_t stream) {
+    H3D_REQUIRE(n_reps >= 1 && n_reps <= H3D_MAX_REPS, "n_reps out of range");
+    H3D_REQUIRE(norm >= 0 && norm <= 3, "unknown norm");
+    H3D_REQUIRE(n_groups == h3d_sf_num_groups(dist_max, n_bins, norm), "n_groups does not match the mode");
+    return sf_table(red, gstart, key_start, n_groups, n_reps, dist_max, n_bins, norm, sf_table_out,
+                    ws, ws_bytes, (cudaStream_t)stream);
 }

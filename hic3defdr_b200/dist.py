@@ -16,6 +16,13 @@ How the path shards:
     tested pixel over NVLink) to the owner of their value range, local ranking
     with global rank offsets, all-gather of one carry per rank, q-values back
     by the mirrored all-to-all.
+  * a chromosome too large (or too alone) for one GPU is sharded by ROW RANGE
+    (``row_ranges``): union, scaling, LRT stay local; only the size factors
+    need the whole chromosome -> ``sharded_size_factor_table``: all-gather of
+    the per-distance pixel counts (fixes every pixel's chromosome-wide rank and
+    so its equal-count bin), one all-to-all of the per-pixel ratios to the
+    owner of their bin, exact medians there, all-gather of the (bins, R)
+    medians.
 Single-process runs take none of these branches.
 """
 import numpy as np
@@ -62,6 +69,21 @@ def shard_chroms(chroms, weight_fn):
     return [c for c, o in zip(chroms, owner) if o == rank()]
 
 
+def row_ranges(weight_per_row, n_ranks=None):
+    """Row range [lo, hi) of every rank for a row-sharded chromosome: cuts the
+    rows where the cumulative weight (stored entries per row, summed over the
+    replicates) crosses k / n_ranks of the total.  Returns (n_ranks + 1,) int64
+    boundaries, identical on every rank."""
+    ws = world_size() if n_ranks is None else n_ranks
+    w = np.asarray(weight_per_row, dtype=np.float64)
+    n = len(w)
+    cum = np.concatenate([[0.0], np.cumsum(w)])
+    if cum[-1] <= 0:
+        return np.linspace(0, n, ws + 1).astype(np.int64)
+    cuts = np.searchsorted(cum, cum[-1] * np.arange(1, ws) / ws, side='left')
+    return np.concatenate([[0], np.minimum(cuts, n), [n]]).astype(np.int64)
+
+
 def _all_gather_counts(local_counts):
     t = torch.from_numpy(np.ascontiguousarray(local_counts, dtype=np.int64))
     if td.get_backend() == 'nccl':
@@ -79,6 +101,8 @@ def regroup_positions(recv_counts, device):
     ``pos = arange + repeat(T - R)`` -- no sort, no host-side expansion."""
     c = np.asarray(recv_counts, dtype=np.int64)               # (ws, owned)
     n = int(c.sum())
+    if n == 0:
+        return torch.empty(0, dtype=torch.int64, device=device)
     flat = c.ravel()                                          # arrival order
     r_start = np.concatenate([[0], np.cumsum(flat)[:-1]])
     t_start = np.concatenate([[0], np.cumsum(c.T.ravel())[:-1]]) \
@@ -263,3 +287,93 @@ def global_bh(local_p, bh_fn=None, bh_ranked_fn=None, carry_fn=None):
     td.all_to_all_single(back, q_bucket, output_split_sizes=send_splits,
                          input_split_sizes=recv_splits)
     return back[pos] if n else back
+
+
+def _coll_tensor(a, like=None):
+    """numpy -> tensor on the device the collectives of this backend use"""
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    return t.cuda() if td.get_backend() == 'nccl' else t
+
+
+def sharded_size_factor_table(balanced, dist, dist_max, n_bins, norm,
+                              kernels=None):
+    """Size-factor table (hic3defdr/util/scaling.py:27-149 with equal_bin,
+    util/binning.py:4-25) of ONE chromosome whose union pixels are sharded
+    over the ranks by row range: ``balanced`` (n_local, R) and ``dist``
+    (n_local,) are this rank's pixels, rank order = row order.  Every rank
+    returns the same table as ``ops.size_factor_table`` gives on the whole
+    chromosome (medians are order statistics, so bit for bit; the sums of the
+    scaling norms in a different summation order), or None if the chromosome
+    has no pixels at all.
+
+    ``kernels``: the per-stage arithmetic (default hic3defdr_b200.ops, i.e.
+    libh3d; the CPU gloo test passes numpy stand-ins)."""
+    if kernels is None:
+        from hic3defdr_b200 import ops as kernels
+    K = kernels
+    ws, me = world_size(), rank()
+    conditional = 'conditional' in norm
+    nb = int(n_bins or 0) if conditional else 0
+    n_local, n_reps = int(balanced.shape[0]), int(balanced.shape[1])
+    n_groups = K.sf_num_groups(dist_max, nb, norm)
+    # 1. chromosome-wide position of every local pixel in (distance, row) order
+    if conditional:
+        if n_local:
+            rank_local, ks_local = K.stable_rank(dist, dist_max + 1)
+            cnt_local = np.diff(np.asarray(ks_local.cpu()))
+        else:
+            rank_local, cnt_local = None, np.zeros(dist_max + 1, np.int64)
+    else:
+        rank_local, cnt_local = None, np.array([n_local], dtype=np.int64)
+    all_cnt = _all_gather_counts(cnt_local)                 # (ws, keys)
+    key_start = np.concatenate([[0], np.cumsum(all_cnt.sum(axis=0))]) \
+        .astype(np.int64)
+    n_total = int(key_start[-1])
+    if n_total == 0:
+        return None
+    my_off = key_start[:-1] + all_cnt[:me].sum(axis=0)      # (keys,)
+    cnt_me = all_cnt[me]
+    # 2. equal-count bins are ranges of the chromosome-wide order; the local
+    # pixels of a bin are a contiguous range of the local distance order too
+    gstart = np.asarray(K.sf_group_bounds(
+        n_total, dist_max, nb, norm,
+        key_start if conditional else None).cpu()).astype(np.int64)
+    below = np.clip(gstart[:, None] - my_off[None, :], 0, cnt_me[None, :])
+    lb = below.sum(axis=1).astype(np.int64)                 # (n_groups + 1,)
+    # 3. ratios in local distance order, sent to the owners of their bins
+    values = K.sf_values(balanced, rank_local, norm)        # (R, n_local)
+    gk = (np.arange(ws + 1) * n_groups) // ws               # owner k: [gk[k], gk[k+1])
+    send_splits = [int(lb[gk[k + 1]] - lb[gk[k]]) for k in range(ws)]
+    all_lc = _all_gather_counts(np.diff(lb))                # (ws, n_groups)
+    recv_counts = all_lc[:, gk[me]:gk[me + 1]]              # (ws, own)
+    recv_splits = [int(c.sum()) for c in recv_counts]
+    n_recv = int(sum(recv_splits))
+    recv = torch.empty((n_reps, max(n_recv, 1)), dtype=values.dtype,
+                       device=values.device)
+    works = [td.all_to_all_single(
+        recv[r, :n_recv], values[r, :n_local],
+        output_split_sizes=recv_splits, input_split_sizes=send_splits,
+        async_op=True) for r in range(n_reps)]
+    pos = regroup_positions(recv_counts, values.device)     # -> [bin][source]
+    for w in works:
+        w.wait()
+    grouped = torch.empty_like(recv)
+    if n_recv:
+        grouped[:, pos] = recv[:, :n_recv]
+    own_start = np.concatenate([[0], np.cumsum(recv_counts.sum(axis=0))]) \
+        .astype(np.int64)
+    # 4. exact medians (sums) of the owned bins, shared with every rank
+    n_own_max = int(np.max(np.diff(gk)))
+    red_own = torch.zeros((max(n_own_max, 1), n_reps), dtype=values.dtype,
+                          device=values.device)
+    n_own = int(gk[me + 1] - gk[me])
+    if n_own:
+        red, _ = K.sf_group_reduce(grouped, own_start, norm)
+        red_own[:n_own] = red
+    parts = [torch.empty_like(red_own) for _ in range(ws)]
+    td.all_gather(parts, red_own)
+    red_all = torch.cat([p[:int(gk[k + 1] - gk[k])]
+                         for k, p in enumerate(parts)])
+    # 5. bin means and interpolation over distance, redundantly
+    return K.sf_table(red_all, gstart, key_start if conditional else None,
+                      dist_max, nb, norm)

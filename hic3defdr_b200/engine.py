@@ -69,6 +69,51 @@ def prepare_chrom(csr, bias_raw, design, *args, **kw):
         return stop.value
 
 
+def _empty_prepared(st, n_reps, balanced):
+    st.update(size_factors=torch.empty((0, n_reps), dtype=torch.float64,
+                                       device='cuda'),
+              scaled=balanced,
+              disp_idx=torch.empty(0, dtype=torch.uint8, device='cuda'),
+              disp_index=torch.empty(0, dtype=torch.int32, device='cuda'))
+    return st
+
+
+def prepare_chrom_sharded(csr, bias_raw, design, dist_min=4, dist_max=200,
+                          bias_thresh=0.1, mean_thresh=1.0,
+                          norm='conditional_mor', n_bins=-1, loop_pixels=None):
+    """``prepare_chrom`` for a chromosome sharded over the ranks by row range
+    (BASELINE config 4): ``csr`` holds this rank's rows
+    only (``staging.shard_rows``), ``bias_raw`` the whole chromosome's bias.
+    Union, gathers, scaling and the filter are local to the row range; the
+    size factors are the chromosome's (``dist.sharded_size_factor_table``), so
+    every rank must call this for the same chromosomes in the same order.
+    The state holds this rank's pixels; the ranks' states concatenated in rank
+    order are the single-GPU state."""
+    if n_bins == -1:
+        n_bins = int(dist_max / 5)
+    bias = ops.filter_bias(bias_raw, bias_thresh)
+    u = ops.union_gather(csr, dist_max, bias)
+    n_px = int(u['row'].numel())
+    st = dict(bias=bias, row=u['row'], col=u['col'], raw=u['raw'])
+    table = hdist.sharded_size_factor_table(u['balanced'], u['dist'], dist_max,
+                                            n_bins, norm)
+    if n_px == 0 or table is None:
+        if 'conditional' not in norm and table is not None:
+            _empty_prepared(st, csr.n_reps, u['balanced'])
+            st['size_factors'] = table
+            return st
+        return _empty_prepared(st, csr.n_reps, u['balanced'])
+    scaled, sf, disp_idx = ops.scale_filter(
+        u['row'], u['col'], u['balanced'], table, design, dist_max,
+        mean_thresh, dist_min)
+    st.update(size_factors=sf, scaled=scaled, disp_idx=disp_idx,
+              disp_index=ops.mask_to_index(disp_idx))
+    if loop_pixels is not None:
+        st['loop_idx'] = ops.loop_membership(st['row'], st['col'],
+                                             st['disp_index'], loop_pixels)
+    return st
+
+
 _PREPARE_STREAMS = {}
 
 
@@ -282,21 +327,31 @@ def run_to_qvalues(chrom_inputs, design, dist_min=4, dist_max=200,
                    bias_thresh=0.1, mean_thresh=1.0, norm='conditional_mor',
                    n_bins=-1, estimator='qcml', frac=None,
                    auto_frac_factor=15., weighted_lowess=True, refit_mu=True,
-                   sink=None):
+                   sink=None, row_sharded=False):
     """All four steps on device inputs: ``chrom_inputs`` is an iterable of
     (ops.DeviceCSR, bias_raw CUDA tensor) for THIS rank's chromosomes (a list,
     or a ``staging.InputPrefetcher`` that uploads ahead of the kernels).
     ``sink(i, name, tensor)``, if given, is called for every output array of
     chromosome i as soon as it is final (``staging.OutputDrain`` starts its
     device -> host copy there).
+    ``row_sharded``: every rank holds a row range of EVERY chromosome
+    (``staging.shard_rows``) instead of whole chromosomes; the states are then
+    this rank's pixels of each chromosome.
     Returns (states, disp_per_dist, trend callables, qcml stats)."""
     design = np.asarray(design).astype(bool)
     emit = sink if sink is not None else (lambda i, name, t: None)
     with stage('prepare_data'):
-        states = prepare_many(chrom_inputs, design, sink=sink,
-                              dist_min=dist_min, dist_max=dist_max,
-                              bias_thresh=bias_thresh, mean_thresh=mean_thresh,
-                              norm=norm, n_bins=n_bins)
+        kw = dict(dist_min=dist_min, dist_max=dist_max,
+                  bias_thresh=bias_thresh, mean_thresh=mean_thresh, norm=norm,
+                  n_bins=n_bins)
+        if row_sharded and hdist.world_size() > 1:
+            states = []
+            for i, (csr, b) in enumerate(chrom_inputs):
+                states.append(prepare_chrom_sharded(csr, b, design, **kw))
+                for k in PREPARE_OUTPUTS:
+                    emit(i, k, states[-1][k])
+        else:
+            states = prepare_many(chrom_inputs, design, sink=sink, **kw)
     with stage('estimate_disp'):
         dpd, fns, stats = estimate_disp(states, design, dist_max,
                                         estimator=estimator, frac=frac,

@@ -252,6 +252,68 @@ def size_factor_table(balanced, dist, dist_max, n_bins, norm):
     return table
 
 
+# the stages of ``size_factor_table`` one by one: hic3defdr_b200.dist puts the
+# collectives between them when a chromosome is sharded by row range
+def sf_num_groups(dist_max, n_bins, norm):
+    return int(lib().query('h3d_sf_num_groups', int(dist_max),
+                           int(n_bins or 0), NORMS[norm]))
+
+
+def sf_group_bounds(n_total, dist_max, n_bins, norm, key_start):
+    """First position (chromosome-wide distance order) of every equal-count
+    bin (util/binning.py:4-25) -> (n_groups + 1,) int64 CUDA tensor."""
+    n_groups = sf_num_groups(dist_max, n_bins, norm)
+    ks = dev(key_start, torch.int64) if key_start is not None else None
+    gstart = torch.empty(n_groups + 1, dtype=torch.int64, device='cuda')
+    lib().call('h3d_sf_group_bounds', int(n_total), int(dist_max),
+               int(n_bins or 0), NORMS[norm], ptr(ks), ptr(gstart), _stream())
+    return gstart
+
+
+def sf_values(balanced, rank, norm):
+    """Per-pixel ratios to the geometric mean over replicates
+    (util/scaling.py:41-47; the plain values for the scaling norms), written
+    replicate-major at position ``rank`` -> (R, n) float64 CUDA tensor."""
+    bal = dev(balanced, torch.float64)
+    n_px, n_reps = bal.shape
+    out = torch.empty((n_reps, n_px), dtype=torch.float64, device='cuda')
+    lib().call('h3d_sf_values', ptr(bal), ptr(rank), n_px, n_reps, NORMS[norm],
+               ptr(out), _stream())
+    return out
+
+
+def sf_group_reduce(values, gstart, norm):
+    """Exact median (sum for the scaling norms) of every (group, replicate)
+    slice of ``values`` (R, ld) -> ((n_groups, R) float64, (n_groups,) int64
+    number of ratios per group)."""
+    n_reps, ld = values.shape
+    gs = dev(gstart, torch.int64)
+    n_groups = gs.numel() - 1
+    red = torch.empty((n_groups, n_reps), dtype=torch.float64, device='cuda')
+    valid = torch.zeros(max(n_groups, 1), dtype=torch.int64, device='cuda')
+    lib().call('h3d_sf_group_reduce', ptr(values), int(ld), ptr(gs), n_groups,
+               n_reps, NORMS[norm], ptr(red), ptr(valid), _stream())
+    return red, valid[:n_groups]
+
+
+def sf_table(red, gstart, key_start, dist_max, n_bins, norm):
+    """util/scaling.py:92-104 (bin means, interpolation over distance) from
+    the per-group reductions -> the table of ``size_factor_table``."""
+    red = dev(red, torch.float64)
+    n_groups, n_reps = red.shape
+    conditional = 'conditional' in norm
+    gs = dev(gstart, torch.int64)
+    ks = dev(key_start, torch.int64) if conditional else None
+    shape = (dist_max + 1, n_reps) if conditional else (n_reps,)
+    table = torch.empty(shape, dtype=torch.float64, device='cuda')
+    wsb = lib().query('h3d_sf_table_ws_bytes', n_groups, n_reps)
+    ws = workspace(wsb)
+    lib().call('h3d_sf_table', ptr(red), ptr(gs), ptr(ks), n_groups, n_reps,
+               int(dist_max), int(n_bins or 0), NORMS[norm], ptr(table),
+               ptr(ws), wsb, _stream())
+    return table
+
+
 def _conditional(data, dist, n_bins, norm):
     d = np.asarray(dist.cpu() if isinstance(dist, torch.Tensor) else dist)
     dist_max = int(d.max())

@@ -41,6 +41,33 @@ def pinned_csr(mats):
                  data=pin(m.data.astype(dtype, copy=False))) for m in out]
 
 
+def row_weights(mats):
+    """stored entries per row, summed over the replicate matrices: the weight
+    ``dist.row_ranges`` balances a row-sharded chromosome by"""
+    import scipy.sparse as sparse
+    return np.sum([np.diff(sparse.csr_matrix(m).indptr) for m in mats], axis=0)
+
+
+def shard_rows(mats, lo, hi):
+    """The rows [lo, hi) of every replicate matrix as CSR matrices of the
+    ORIGINAL shape (the other rows empty): row and column numbers keep their
+    chromosome-wide meaning, only the stored entries of the range are kept
+    (and later uploaded)."""
+    import scipy.sparse as sparse
+    out = []
+    for m in mats:
+        m = sparse.csr_matrix(m)
+        if not m.has_canonical_format:
+            m = m.copy()
+            m.sum_duplicates()
+        a, b = int(m.indptr[lo]), int(m.indptr[hi])
+        indptr = np.clip(m.indptr, a, b) - a
+        out.append(sparse.csr_matrix(
+            (m.data[a:b], m.indices[a:b], indptr.astype(m.indptr.dtype)),
+            shape=m.shape))
+    return out
+
+
 def csr_to_device(host_mats, n_bins):
     """pinned (or device) CSR pieces -> ops.DeviceCSR on the current stream"""
     c = ops.DeviceCSR.__new__(ops.DeviceCSR)

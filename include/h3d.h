@@ -105,6 +105,42 @@ int h3d_size_factors(const int* dist, const double* balanced, long long n_px,
                      h3d_stream_t stream);
 size_t h3d_size_factors_ws_bytes(long long n_px, int n_reps, int dist_max);
 
+/* The stages of h3d_size_factors as separate entry points, for a chromosome
+ * whose union pixels are sharded over several GPUs by row range (SURVEY.md
+ * section 8(e)); hic3defdr_b200/dist.py places the collectives between them:
+ *   every rank ranks its pixels by distance (h3d_stable_rank), the per-
+ *   distance counts are all-gathered, which fixes every pixel's position in
+ *   the chromosome-wide (distance, row, col) order and so its equal-count bin
+ *   (util/binning.py:4-25); bins are owned by ranks; one all-to-all moves the
+ *   per-pixel ratios (util/scaling.py:41-47) to the owner of their bin, which
+ *   takes the exact per-replicate medians; the (bins, n_reps) medians are
+ *   all-gathered and every rank builds the (dist_max + 1, n_reps) table.
+ * n_groups = h3d_sf_num_groups(...): n_bins (conditional norms, n_bins > 0),
+ * dist_max + 1 (conditional, n_bins == 0) or 1.
+ * h3d_sf_group_bounds: gstart[g] = first position (in distance order, over
+ *   n_total pixels) of group g; key_start = (dist_max + 2) boundaries of the
+ *   distances over the same n_total pixels (conditional norms only).
+ * h3d_sf_values: values[r * n_px + rank[p]] = ratio (or balanced value, for
+ *   the scaling norms) of pixel p, replicate r; pixels without a ratio (a
+ *   replicate <= 0) get the all-ones bit pattern, which the reducer skips.
+ * h3d_sf_group_reduce: red[g, r] = median (sum for the scaling norms) of
+ *   values[r * ld + gstart[g] .. gstart[g + 1]); valid[g] = ratios in g.
+ * h3d_sf_table: the table of h3d_size_factors from red, gstart, key_start. */
+int h3d_sf_num_groups(int dist_max, int n_bins, int norm);
+int h3d_sf_group_bounds(long long n_total, int dist_max, int n_bins, int norm,
+                        const long long* key_start, long long* gstart,
+                        h3d_stream_t stream);
+int h3d_sf_values(const double* balanced, const int* rank, long long n_px,
+                  int n_reps, int norm, double* values, h3d_stream_t stream);
+int h3d_sf_group_reduce(const double* values, long long ld, const long long* gstart,
+                        int n_groups, int n_reps, int norm, double* red,
+                        long long* valid, h3d_stream_t stream);
+int h3d_sf_table(const double* red, const long long* gstart,
+                 const long long* key_start, int n_groups, int n_reps, int dist_max,
+                 int n_bins, int norm, double* sf_table, void* ws, size_t ws_bytes,
+                 h3d_stream_t stream);
+size_t h3d_sf_table_ws_bytes(int n_groups, int n_reps);
+
 /* scaled = balanced / size_factors, per-condition means and disp_idx,
  * hic3defdr/analysis/analysis.py:109-115.  ``data`` holds balanced on entry
  * and scaled on exit.  size_factors_out ((n_px, n_reps)) may be NULL.

@@ -121,6 +121,159 @@ def _worker(rank, world, port, ret):
         td.destroy_process_group()
 
 
+class _NumpyStages(object):
+    """numpy stand-ins for the libh3d stages that
+    ``dist.sharded_size_factor_table`` chains (same layouts and conventions as
+    hic3defdr_b200/ops.py: sf_num_groups ... sf_table)."""
+
+    @staticmethod
+    def _conditional(norm):
+        return 'conditional' in norm
+
+    def sf_num_groups(self, dist_max, n_bins, norm):
+        if not self._conditional(norm):
+            return 1
+        return n_bins if n_bins else dist_max + 1
+
+    def stable_rank(self, keys, n_keys):
+        k = np.asarray(keys)
+        order = np.argsort(k, kind='stable')
+        rank = np.empty(len(k), dtype=np.int64)
+        rank[order] = np.arange(len(k))
+        start = np.concatenate([[0], np.cumsum(np.bincount(k, minlength=n_keys))])
+        return torch.from_numpy(rank), torch.from_numpy(start)
+
+    def sf_group_bounds(self, n_total, dist_max, n_bins, norm, key_start):
+        if not self._conditional(norm):
+            return torch.tensor([0, n_total])
+        if not n_bins:
+            return torch.from_numpy(np.asarray(key_start[:dist_max + 2]))
+        idx = np.linspace(0, n_bins, n_total, endpoint=0, dtype=int)
+        return torch.from_numpy(np.searchsorted(idx, np.arange(n_bins + 1)))
+
+    def sf_values(self, balanced, rank, norm):
+        b = np.asarray(balanced)
+        out = np.empty(b.shape[::-1])
+        if norm in ('conditional_mor', 'median_of_ratios'):
+            gm = np.exp(np.mean(np.log(b + 1), axis=1)) - 1
+            with np.errstate(all='ignore'):
+                v = b / gm[:, None]
+            v[~np.all(b > 0, axis=1)] = np.nan
+        else:
+            v = b
+        pos = np.arange(len(b)) if rank is None else np.asarray(rank)
+        out[:, pos] = v.T
+        return torch.from_numpy(out)
+
+    def sf_group_reduce(self, values, gstart, norm):
+        v = values.numpy()
+        g = np.asarray(gstart)
+        red = np.full((len(g) - 1, v.shape[0]), np.nan)
+        for i in range(len(g) - 1):
+            seg = v[:, g[i]:g[i + 1]]
+            if norm in ('conditional_mor', 'median_of_ratios'):
+                ok = ~np.isnan(seg[0])
+                if ok.any():
+                    red[i] = np.median(seg[:, ok], axis=1)
+            else:
+                red[i] = seg.sum(axis=1)
+        return torch.from_numpy(red), None
+
+    def sf_table(self, red, gstart, key_start, dist_max, n_bins, norm):
+        from oracle import pipeline as op
+        from oracle.thirdparty import gmean
+        red, g = red.numpy(), np.asarray(gstart)
+        occ = np.diff(g) > 0
+        s_b = red[occ]
+        if 'scaling' in norm:
+            s_b = s_b / np.array([gmean(row) for row in s_b])[:, None]
+        if not self._conditional(norm):
+            return torch.from_numpy(s_b[0])
+        d_of = np.repeat(np.arange(dist_max + 1), np.diff(key_start))
+        d_b = np.array([d_of[g[i]:g[i + 1]].mean()
+                        for i in range(len(g) - 1) if occ[i]])
+        x = np.arange(dist_max + 1)
+        if not n_bins:
+            table = np.full((dist_max + 1, red.shape[1]), np.nan)
+            table[occ] = s_b
+            return torch.from_numpy(table)
+        return torch.from_numpy(np.stack(
+            [op.interp_extrap(d_b, s_b[:, r], x)
+             for r in range(red.shape[1])], axis=1))
+
+
+def _sf_worker(rank, world, port, ret):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    td.init_process_group('gloo', rank=rank, world_size=world)
+    from hic3defdr_b200 import dist as hd
+    from oracle import pipeline as op
+    try:
+        # one chromosome: pixels in (row, col) order, cut by row range
+        rng = np.random.default_rng(77)                 # same on every rank
+        n_rows, dist_max, n_reps = 400, 30, 4
+        row = np.repeat(np.arange(n_rows), dist_max + 1)
+        col = row + np.tile(np.arange(dist_max + 1), n_rows)
+        keep = (col < n_rows) & (rng.random(len(row)) < 0.8)
+        row, col = row[keep], col[keep]
+        dist = (col - row).astype(np.int32)
+        bal = rng.gamma(2.0, 40.0 / (1 + dist)[:, None], (len(row), n_reps))
+        bal[rng.random(bal.shape) < 0.05] = 0.0          # pixels without a ratio
+        w = np.bincount(row, minlength=n_rows)
+        bounds = hd.row_ranges(w)
+        assert bounds[0] == 0 and bounds[-1] == n_rows and \
+            (np.diff(bounds) >= 0).all()
+        if world == 3:           # a rank without a single pixel must still take part
+            bounds = np.array([0, 150, 150, n_rows])
+        mine = (row >= bounds[rank]) & (row < bounds[rank + 1])
+        for norm, n_bins in (('conditional_mor', 6), ('conditional_mor', 0),
+                             ('conditional_scaling', 5),
+                             ('median_of_ratios', 0), ('simple_scaling', 0)):
+            table = hd.sharded_size_factor_table(
+                torch.from_numpy(bal[mine]), torch.from_numpy(dist[mine]),
+                dist_max, n_bins, norm, kernels=_NumpyStages()).numpy()
+            if norm == 'median_of_ratios':
+                np.testing.assert_array_equal(table, op.median_of_ratios(bal))
+                continue
+            if norm == 'simple_scaling':
+                np.testing.assert_allclose(table, op.simple_scaling(bal),
+                                           rtol=1e-12)
+                continue
+            reducer = op.median_of_ratios if norm.endswith('mor') else \
+                op.simple_scaling
+            want = op.conditional_size_factors(bal, dist, n_bins, reducer)
+            got = table[dist]
+            if norm.endswith('mor'):
+                np.testing.assert_array_equal(got, want)
+            else:
+                np.testing.assert_allclose(got, want, rtol=1e-12)
+        # a chromosome without any pixel
+        assert hd.sharded_size_factor_table(
+            torch.empty((0, n_reps), dtype=torch.float64),
+            torch.empty(0, dtype=torch.int32), dist_max, 6,
+            'conditional_mor', kernels=_NumpyStages()) is None
+        ret[rank] = 'ok'
+    except Exception:
+        import traceback
+        ret[rank] = traceback.format_exc()
+    finally:
+        td.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_row_sharded_size_factors(world):
+    """SURVEY.md section 8(e), pixel-range sharding of one chromosome: the
+    collectives of ``dist.sharded_size_factor_table`` (counts all-gather, bin
+    owner all-to-all, medians all-gather) reproduce the whole-chromosome size
+    factors of the oracle, bit for bit for the median-based norms."""
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_sf_worker, args=(world, _free_port(), ret), nprocs=world,
+             join=True)
+    for r in range(world):
+        assert ret.get(r) == 'ok', ret.get(r)
+
+
 @pytest.mark.parametrize('world', [2, 3])
 def test_multi_rank_host_logic(world):
     mgr = mp.Manager()

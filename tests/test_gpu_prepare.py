@@ -162,3 +162,45 @@ def test_union_empty_and_int32_data():
     u = ops.union_gather(ops.DeviceCSR([m, empty.astype(np.int32)]), 10, None)
     np.testing.assert_array_equal(u['row'].cpu().numpy(), row)
     np.testing.assert_array_equal(u['col'].cpu().numpy(), col)
+
+
+@pytest.mark.parametrize('norm,n_bins', [
+    ('conditional_mor', 8), ('conditional_mor', 0), ('conditional_scaling', 8),
+    ('median_of_ratios', 0), ('simple_scaling', 0)])
+def test_size_factor_stages_equal_the_fused_call(norm, n_bins):
+    """h3d_sf_group_bounds / _values / _group_reduce / _table (the entry
+    points the row-sharded path chains with collectives in between) against
+    h3d_size_factors and against the oracle, on one device."""
+    from hic3defdr_b200 import ops
+    from hic3defdr_b200.synth import make_chrom
+    dist_max = 40
+    mats, bias, _ = make_chrom(600, 4, dist_max, seed=991, amp=250.0)
+    u = ops.union_gather(ops.DeviceCSR(mats), dist_max,
+                         ops.filter_bias(bias, 0.1))
+    bal, dist = u['balanced'], u['dist']
+    want = ops.size_factor_table(bal, dist, dist_max, n_bins, norm)
+    conditional = 'conditional' in norm
+    rank, key_start = (ops.stable_rank(dist, dist_max + 1) if conditional
+                       else (None, None))
+    gstart = ops.sf_group_bounds(bal.shape[0], dist_max, n_bins, norm,
+                                 key_start)
+    assert gstart.numel() == ops.sf_num_groups(dist_max, n_bins, norm) + 1
+    values = ops.sf_values(bal, rank, norm)
+    red, valid = ops.sf_group_reduce(values, gstart, norm)
+    got = ops.sf_table(red, gstart, key_start, dist_max, n_bins, norm)
+    np.testing.assert_array_equal(got.cpu().numpy(), want.cpu().numpy())
+    b, d = bal.cpu().numpy(), dist.cpu().numpy()
+    if conditional:
+        reducer = op.median_of_ratios if norm.endswith('mor') else \
+            op.simple_scaling
+        ref = op.conditional_size_factors(b, d, n_bins, reducer)
+        np.testing.assert_allclose(got.cpu().numpy()[d], ref, rtol=1e-12)
+        if norm.endswith('mor') and n_bins:
+            bins = op.equal_bin(d, n_bins)
+            n_ok = [int(np.all(b[bins == g] > 0, axis=1).sum())
+                    for g in range(n_bins)]
+            assert valid.cpu().numpy().tolist() == n_ok
+    else:
+        ref = op.median_of_ratios(b) if norm == 'median_of_ratios' else \
+            op.simple_scaling(b)
+        np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=1e-12)
