@@ -36,7 +36,7 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 if REPO not in sys.path:
     sys.path.insert(0, REPO)
 
-from hic3defdr_b200.synth import MM10_10KB  # noqa: E402
+from hic3defdr_b200.synth import HG38_5KB, HG38_CHR1_1KB, MM10_10KB  # noqa: E402
 
 # SURVEY.md section 8(d), cost model v1: FP64 instruction-equivalents of one
 # pixel-equalisation (fit_mu_hat 500 + gmean 85 + 2 x q2q 2150) for R_c = 2;
@@ -51,6 +51,16 @@ WORKLOADS = {
                      n_reps=4, dist_max=200, amp=300.0,
                      desc='synthetic 2-vs-2 reps, chr18+chr19 mouse-sized, '
                           '10 kb, dist cap 200 bins'),
+    # BASELINE.json configs[2] / configs[3]: not the headline (bench lines are
+    # quoted on mouse10kb); here so that their shapes can be timed on request
+    'human5kb': dict(chroms=HG38_5KB, n_reps=8, dist_max=200, amp=150.0,
+                     res_scale=2.0,
+                     desc='synthetic human genome-wide 5 kb, 4-vs-4 reps, '
+                          "trend='dist' dispersion"),
+    'chr1_1kb': dict(chroms=HG38_CHR1_1KB, n_reps=4, dist_max=2000, amp=30.0,
+                     res_scale=10.0,
+                     desc='synthetic human chr1 at 1 kb, 2-vs-2 reps, dist cap '
+                          '2 Mb (single large chromosome, pixel-range sharded)'),
     'tiny': dict(chroms={'chrA': 1500, 'chrB': 1100}, n_reps=4, dist_max=60,
                  amp=200.0, desc='tiny smoke workload'),
 }
@@ -65,7 +75,7 @@ REF_SAMPLE = dict(chroms={'s%d' % i: 520 + 10 * i for i in range(20)},
 # synthetic inputs, generated on the device (same sampling model as
 # hic3defdr_b200/synth.py; plumbing, outside every timed region)
 # --------------------------------------------------------------------------
-def gen_chrom_device(n, n_reps, dist_max, seed, amp, pad=5):
+def gen_chrom_device(n, n_reps, dist_max, seed, amp, pad=5, res_scale=1.0):
     import torch
     g = torch.Generator(device='cuda').manual_seed(seed)
     width = dist_max + pad + 1
@@ -74,7 +84,7 @@ def gen_chrom_device(n, n_reps, dist_max, seed, amp, pad=5):
     col = row[:, None] + torch.arange(width, device='cuda')[None, :]
     valid = col < n
     mu = (amp / (1.0 + d))[None, :]
-    phi = (0.01 + 1e-4 * d)[None, :]
+    phi = (0.01 + 1e-4 * d * res_scale)[None, :]
     bias = torch.exp(0.2 * torch.randn((n, n_reps), generator=g, device='cuda',
                                        dtype=torch.float64))
     bad = torch.rand((n, n_reps), generator=g, device='cuda') < 0.01
@@ -94,7 +104,20 @@ def gen_chrom_device(n, n_reps, dist_max, seed, amp, pad=5):
         mats.append(dict(indptr=indptr.to(torch.int32),
                          indices=col[keep].to(torch.int32),
                          data=x[keep].to(torch.int64)))
+        del m, shape, lam, x, keep
     return mats, bias
+
+
+def shard_rows_device(mats, lo, hi):
+    """device form of staging.shard_rows: the stored entries of rows [lo, hi)
+    only, row / column numbers unchanged"""
+    out = []
+    for m in mats:
+        a, b = int(m['indptr'][lo]), int(m['indptr'][hi])
+        out.append(dict(indptr=(m['indptr'].clamp(a, b) - a),
+                        indices=m['indices'][a:b].clone(),
+                        data=m['data'][a:b].clone()))
+    return out
 
 
 class HostChrom(object):
@@ -239,6 +262,9 @@ def main():
     ap.add_argument('--impl', default='b200')
     ap.add_argument('--workload', default='mouse10kb')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--shard', default='chroms', choices=('chroms', 'rows'),
+                    help='multi-GPU partition: whole chromosomes per rank, or '
+                         'a row range of every chromosome per rank')
     args = ap.parse_args()
     cfg = WORKLOADS[args.workload]
     if args.impl == 'reference':
@@ -257,8 +283,11 @@ def main():
     if world > 1:
         td.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     rank = hdist.rank()
-    design = np.array([[1, 0], [1, 0], [0, 1], [0, 1]], dtype=bool)
-    kw = dict(dist_max=cfg['dist_max'])
+    half = cfg['n_reps'] // 2
+    design = np.array([[1, 0]] * half + [[0, 1]] * (cfg['n_reps'] - half),
+                      dtype=bool)
+    row_sharded = args.shard == 'rows' and world > 1
+    kw = dict(dist_max=cfg['dist_max'], row_sharded=row_sharded)
     # NVML is initialised here, long before the timed region: its first
     # queries were followed ~0.4 s later by a one-off 40-500 ms device stall
     sampler = ClockSampler(local_rank)
@@ -267,13 +296,23 @@ def main():
     # ---- inputs: this rank's chromosomes, resident in HBM ---------------
     names = list(cfg['chroms'].keys())
     owner = hdist.lpt_assign([cfg['chroms'][c] for c in names], world)
-    mine = [c for c, o in zip(names, owner) if o == rank]
+    mine = names if row_sharded else \
+        [c for c, o in zip(names, owner) if o == rank]
     dev_inputs, host_inputs = [], []
     for c in mine:
         n = cfg['chroms'][c]
         mats, bias = gen_chrom_device(n, cfg['n_reps'], cfg['dist_max'],
                                       20261018 + 1000 + 100 * names.index(c),
-                                      cfg['amp'])
+                                      cfg['amp'],
+                                      res_scale=cfg.get('res_scale', 1.0))
+        if row_sharded:
+            # every rank generated the same chromosome; it keeps its rows
+            w = sum((m['indptr'][1:] - m['indptr'][:-1]).cpu().numpy()
+                    for m in mats)
+            bounds = hdist.row_ranges(w, world)
+            mats = shard_rows_device(mats, int(bounds[rank]),
+                                     int(bounds[rank + 1]))
+            torch.cuda.empty_cache()
         dev_inputs.append((staging.csr_to_device(mats, n), bias))
         host_inputs.append((HostChrom(mats, bias), n))
     torch.cuda.synchronize()
@@ -407,9 +446,12 @@ def main():
             config=dict(workload=cfg['desc'], union_pixels=int(n_px),
                         disp_pixels=int(n_d), n_reps=cfg['n_reps'],
                         dist_thresh_max=cfg['dist_max'],
-                        sharding='chromosomes dealt to ranks (LPT); '
+                        sharding=('row range of every chromosome per rank, '
+                                  'size factors through an all-to-all by bin '
+                                  'owner; ' if row_sharded else
+                                  'chromosomes dealt to ranks (LPT); ') +
                                  'dispersion pooled by distance (all-to-all); '
-                                 'BH all-gather',
+                                 'BH by distributed sort/rank (all-to-all)',
                         l2='inputs (%.1f GB/step) larger than L2'
                            % (h2d_all / 1e9)),
             e2e=dict(value=n_px / (ms_e2e / args.steps * 1e-3),

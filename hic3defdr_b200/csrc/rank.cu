@@ -55,7 +55,22 @@ static RankPlan make_rank_plan(long long n, int n_keys) {
     return p;
 }
 
-__global__ void rank_hist_kernel(const int* __restrict__ keys, long long n, int n_keys,
+// where a key comes from: an int32 array, or one digit of a 64-bit sort key
+// (the LSD radix passes of bh.cu: no separate digit array, no separate scatter)
+struct IntKeys {
+    const int* __restrict__ keys;
+    __device__ __forceinline__ int operator()(long long i) const { return keys[i]; }
+};
+struct DigitKeys {
+    const unsigned long long* __restrict__ keys;
+    int shift, mask;
+    __device__ __forceinline__ int operator()(long long i) const {
+        return (int)((keys[i] >> shift) & (unsigned long long)mask);
+    }
+};
+
+template <typename KeyFn>
+__global__ void rank_hist_kernel(KeyFn keys, long long n, int n_keys,
                                  int seg_len, int n_segs, int* __restrict__ table,
                                  int* __restrict__ bad_key) {
     extern __shared__ int sh_cnt[];
@@ -67,7 +82,7 @@ __global__ void rank_hist_kernel(const int* __restrict__ keys, long long n, int 
         const long long lo = (long long)seg * seg_len;
         const long long hi = (lo + seg_len < n) ? lo + seg_len : n;
         for (long long i = lo + lane; i < hi; i += 32) {
-            const int k = keys[i];
+            const int k = keys(i);
             if (k < 0 || k >= n_keys) { *bad_key = 1; continue; }
             atomicAdd(&cnt[k], 1);
         }
@@ -77,26 +92,66 @@ __global__ void rank_hist_kernel(const int* __restrict__ keys, long long n, int 
     }
 }
 
-// one block per tile of 32 keys; 32 warps split the segments
-__global__ void __launch_bounds__(1024)
-rank_scan_kernel(int* __restrict__ table, int n_keys, int n_segs, long long* __restrict__ key_total) {
-    __shared__ long long part[32][33];
+// Exclusive scan of the (segment x key) table down the segments, per key.
+// Three small kernels so that every SM takes part whatever the shape (201 keys x
+// 9 k segments for a chromosome, 2048 keys x 9 k segments for a BH pass):
+//   A  grid (key tiles of 32, segment chunks): per-chunk column sums
+//   B  one warp-lane per key: exclusive scan of the chunk sums, key totals
+//   C  grid as A: exclusive scan inside the chunk, offset by the chunk's start
+constexpr int kScanChunks = 64;
+
+__global__ void __launch_bounds__(256)
+rank_scan_sums_kernel(const int* __restrict__ table, int n_keys, int n_segs, int chunk_len,
+                      long long* __restrict__ chunk_sum) {
+    __shared__ long long part[8][33];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int k = blockIdx.x * 32 + lane;
-    const int per = (n_segs + 31) / 32;
-    const int s0 = wid * per, s1 = (s0 + per < n_segs) ? s0 + per : n_segs;
+    const int c0 = blockIdx.y * chunk_len;
+    const int c1 = (c0 + chunk_len < n_segs) ? c0 + chunk_len : n_segs;
+    long long sum = 0;
+    if (k < n_keys)
+        for (int s = c0 + wid; s < c1; s += 8) sum += table[(size_t)s * n_keys + k];
+    part[wid][lane] = sum;
+    __syncthreads();
+    if (wid == 0 && k < n_keys) {
+        long long t = 0;
+        for (int w = 0; w < 8; ++w) t += part[w][lane];
+        chunk_sum[(size_t)blockIdx.y * n_keys + k] = t;
+    }
+}
+
+__global__ void rank_scan_chunks_kernel(long long* __restrict__ chunk_sum, int n_keys, int n_chunks,
+                                        long long* __restrict__ key_total) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_keys) return;
+    long long run = 0;
+    for (int c = 0; c < n_chunks; ++c) {
+        const long long t = chunk_sum[(size_t)c * n_keys + k];
+        chunk_sum[(size_t)c * n_keys + k] = run;
+        run += t;
+    }
+    key_total[k] = run;
+}
+
+__global__ void __launch_bounds__(256)
+rank_scan_apply_kernel(int* __restrict__ table, int n_keys, int n_segs, int chunk_len,
+                       const long long* __restrict__ chunk_sum) {
+    __shared__ long long part[8][33];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int k = blockIdx.x * 32 + lane;
+    const int c0 = blockIdx.y * chunk_len;
+    const int c1 = (c0 + chunk_len < n_segs) ? c0 + chunk_len : n_segs;
+    // warp w owns the contiguous slice [s0, s1) of the chunk
+    const int per = (chunk_len + 7) / 8;
+    const int s0 = c0 + wid * per;
+    const int s1 = (s0 + per < c1) ? s0 + per : c1;
     long long sum = 0;
     if (k < n_keys)
         for (int s = s0; s < s1; ++s) sum += table[(size_t)s * n_keys + k];
     part[wid][lane] = sum;
     __syncthreads();
-    if (wid == 0) {
-        long long run = 0;
-        for (int w = 0; w < 32; ++w) { const long long t = part[w][lane]; part[w][lane] = run; run += t; }
-        if (k < n_keys) key_total[k] = run;
-    }
-    __syncthreads();
-    long long run = part[wid][lane];
+    long long run = (k < n_keys) ? chunk_sum[(size_t)blockIdx.y * n_keys + k] : 0;
+    for (int w = 0; w < wid; ++w) run += part[w][lane];
     if (k < n_keys)
         for (int s = s0; s < s1; ++s) {
             const int t = table[(size_t)s * n_keys + k];
@@ -131,9 +186,27 @@ key_start_kernel(const long long* __restrict__ key_total, int n_keys, long long*
     if (threadIdx.x == 0) key_start[n_keys] = carry;
 }
 
-__global__ void rank_emit_kernel(const int* __restrict__ keys, long long n, int n_keys,
+// what happens with an element's position: stored (stable_rank), or used at
+// once to move the (sort key, payload) pair there (radix pass)
+struct StoreRank {
+    int* __restrict__ rank_out;
+    __device__ __forceinline__ void operator()(long long i, int pos) const { rank_out[i] = pos; }
+};
+struct MovePair {
+    const unsigned long long* __restrict__ keys_in;
+    const int* __restrict__ idx_in;
+    unsigned long long* __restrict__ keys_out;
+    int* __restrict__ idx_out;
+    __device__ __forceinline__ void operator()(long long i, int pos) const {
+        keys_out[pos] = keys_in[i];
+        idx_out[pos] = idx_in[i];
+    }
+};
+
+template <typename KeyFn, typename Sink>
+__global__ void rank_emit_kernel(KeyFn keys, long long n, int n_keys,
                                  int seg_len, int n_segs, const int* __restrict__ table,
-                                 const long long* __restrict__ key_start, int* __restrict__ rank_out) {
+                                 const long long* __restrict__ key_start, Sink sink) {
     extern __shared__ int sh_cnt[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     int* cnt = sh_cnt + (size_t)wid * n_keys;
@@ -147,13 +220,13 @@ __global__ void rank_emit_kernel(const int* __restrict__ keys, long long n, int 
         for (long long base = lo; base < hi; base += 32) {
             const long long i = base + lane;
             const bool valid = i < hi;
-            int k = valid ? keys[i] : -1;
+            int k = valid ? keys(i) : -1;
             if (k < 0 || k >= n_keys) k = -1;
             const unsigned act = __ballot_sync(0xffffffffu, k >= 0);
             if (k >= 0) {
                 const unsigned peers = __match_any_sync(act, k);
                 const int mine = cnt[k] + __popc(peers & lt);
-                rank_out[i] = mine;
+                sink(i, mine);
                 __syncwarp(act);
                 if ((peers >> lane) == 1u) cnt[k] += __popc(peers);   // highest lane of the group
                 __syncwarp(act);
@@ -163,37 +236,66 @@ __global__ void rank_emit_kernel(const int* __restrict__ keys, long long n, int 
     }
 }
 
-int stable_rank_impl(const int* keys, long long n, int n_keys, int* rank_out,
-                            long long* key_start, void* ws, size_t ws_bytes, cudaStream_t st) {
+template <typename KeyFn, typename Sink>
+static int counting_rank(KeyFn keys, Sink sink, long long n, int n_keys, long long* key_start,
+                         void* ws, size_t ws_bytes, cudaStream_t st) {
     H3D_REQUIRE(n >= 0 && n < 2147483647LL, "n out of int32 range");
     H3D_REQUIRE(n_keys >= 1 && n_keys <= 40000, "n_keys out of range");
     const RankPlan p = make_rank_plan(n, n_keys);
     Workspace w(ws, ws_bytes);
     int* table = w.take<int>((size_t)p.n_segs * n_keys);
     long long* key_total = w.take<long long>(n_keys + 1);
+    long long* chunk_sum = w.take<long long>((size_t)kScanChunks * n_keys);
     int* bad = w.take<int>(1);
-    if (!table || !key_total || !bad) { set_error("stable_rank workspace too small"); return H3D_ERR_WORKSPACE; }
+    if (!table || !key_total || !chunk_sum || !bad) { set_error("stable_rank workspace too small"); return H3D_ERR_WORKSPACE; }
     H3D_CHECK(cudaMemsetAsync(bad, 0, sizeof(int), st));
     const int threads = p.warps_per_block * 32;
     int grid = div_up(p.n_segs, p.warps_per_block);
     if (p.smem_bytes > 48 * 1024) {
-        H3D_CHECK(cudaFuncSetAttribute(rank_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
-        H3D_CHECK(cudaFuncSetAttribute(rank_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
+        H3D_CHECK(cudaFuncSetAttribute(rank_hist_kernel<KeyFn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
+        H3D_CHECK(cudaFuncSetAttribute(rank_emit_kernel<KeyFn, Sink>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
     }
-    rank_hist_kernel<<<grid, threads, p.smem_bytes, st>>>(keys, n, n_keys, p.seg_len, p.n_segs, table, bad);
+    rank_hist_kernel<KeyFn><<<grid, threads, p.smem_bytes, st>>>(keys, n, n_keys, p.seg_len, p.n_segs, table, bad);
     H3D_LAUNCHED("rank_hist_kernel");
-    rank_scan_kernel<<<div_up(n_keys, 32), 1024, 0, st>>>(table, n_keys, p.n_segs, key_total);
-    H3D_LAUNCHED("rank_scan_kernel");
+    {
+        int n_chunks = kScanChunks;
+        if (n_chunks > p.n_segs) n_chunks = p.n_segs;
+        const int chunk_len = div_up(p.n_segs, n_chunks);
+        n_chunks = div_up(p.n_segs, chunk_len);
+        dim3 sgrid(div_up(n_keys, 32), n_chunks);
+        rank_scan_sums_kernel<<<sgrid, 256, 0, st>>>(table, n_keys, p.n_segs, chunk_len, chunk_sum);
+        H3D_LAUNCHED("rank_scan_sums_kernel");
+        rank_scan_chunks_kernel<<<div_up(n_keys, 128), 128, 0, st>>>(chunk_sum, n_keys, n_chunks, key_total);
+        H3D_LAUNCHED("rank_scan_chunks_kernel");
+        rank_scan_apply_kernel<<<sgrid, 256, 0, st>>>(table, n_keys, p.n_segs, chunk_len, chunk_sum);
+        H3D_LAUNCHED("rank_scan_apply_kernel");
+    }
     key_start_kernel<<<1, 1024, 0, st>>>(key_total, n_keys, key_start);
     H3D_LAUNCHED("key_start_kernel");
-    rank_emit_kernel<<<grid, threads, p.smem_bytes, st>>>(keys, n, n_keys, p.seg_len, p.n_segs, table, key_start, rank_out);
+    rank_emit_kernel<KeyFn, Sink><<<grid, threads, p.smem_bytes, st>>>(keys, n, n_keys, p.seg_len, p.n_segs, table, key_start, sink);
     H3D_LAUNCHED("rank_emit_kernel");
     return H3D_OK;
 }
 
+int stable_rank_impl(const int* keys, long long n, int n_keys, int* rank_out,
+                     long long* key_start, void* ws, size_t ws_bytes, cudaStream_t st) {
+    return counting_rank(IntKeys{keys}, StoreRank{rank_out}, n, n_keys, key_start, ws, ws_bytes, st);
+}
+
+// one stable LSD radix pass over (64-bit key, int payload) pairs on the digit
+// (key >> shift) & (2^bits - 1); workspace as stable_rank_ws(n, 2^bits)
+int radix_pass_u64(const unsigned long long* keys_in, const int* idx_in, long long n, int shift,
+                   int bits, unsigned long long* keys_out, int* idx_out, long long* key_start,
+                   void* ws, size_t ws_bytes, cudaStream_t st) {
+    return counting_rank(DigitKeys{keys_in, shift, (1 << bits) - 1},
+                         MovePair{keys_in, idx_in, keys_out, idx_out}, n, 1 << bits, key_start,
+                         ws, ws_bytes, st);
+}
+
 size_t stable_rank_ws(long long n, int n_keys) {
     const RankPlan p = make_rank_plan(n, n_keys);
-    return ws_pad(p.table_bytes) + ws_pad((size_t)(n_keys + 1) * 8) + ws_pad(4);
+    return ws_pad(p.table_bytes) + ws_pad((size_t)(n_keys + 1) * 8) +
+           ws_pad((size_t)kScanChunks * n_keys * 8) + ws_pad(4);
 }
 
 // --------------------------------------------------------------------------
@@ -250,13 +352,16 @@ ratio_scatter_kernel(const double* __restrict__ balanced, const int* __restrict_
 }
 
 // Exact median of one (group, replicate) slice by MSD radix select.
-// grid = (n_groups, n_reps), 1024 threads, 64 KB dynamic shared memory.
-__global__ void __launch_bounds__(1024)
+// grid = (n_groups, n_reps), NT threads, 64 KB dynamic shared memory.  NT = 512
+// lets two CTAs share an SM: the 160 CTAs of a chromosome (40 bins x 4
+// replicates) then run as one wave on 148 SMs instead of one and a tail.
+template <int NT>
+__global__ void __launch_bounds__(NT)
 median_select_kernel(const unsigned long long* __restrict__ sorted, long long n,
                      const long long* __restrict__ gstart, double* __restrict__ med_out,
                      long long* __restrict__ valid_out, int n_reps) {
     extern __shared__ unsigned hist[];          // [2][8192]
-    __shared__ unsigned scan_part[1024];
+    __shared__ unsigned scan_part[NT];
     __shared__ unsigned long long prefix[2];
     __shared__ long long kth[2];
     __shared__ int done_digit[2];
@@ -268,13 +373,13 @@ median_select_kernel(const unsigned long long* __restrict__ sorted, long long n,
     if (t < 2) { prefix[t] = 0; kth[t] = 0; }
     long long m_valid = 0;
     for (int pass = 0; pass < 5; ++pass) {
-        for (int b = t; b < 2 * 8192; b += 1024) hist[b] = 0;
+        for (int b = t; b < 2 * 8192; b += NT) hist[b] = 0;
         __syncthreads();
         const int sh = shifts[pass], wd = widths[pass];
         const unsigned long long p0 = prefix[0], p1 = prefix[1];
         const unsigned dmask = (1u << wd) - 1u;
         const bool same = (p0 == p1);
-        for (long long i = lo + t; i < hi; i += 1024) {
+        for (long long i = lo + t; i < hi; i += NT) {
             const unsigned long long key = seg[i];
             const unsigned long long hi_bits = (pass == 0) ? 0ull : (key >> (sh + wd));
             const unsigned dg = (unsigned)(key >> sh) & dmask;
@@ -292,12 +397,12 @@ median_select_kernel(const unsigned long long* __restrict__ sorted, long long n,
         // locate the digit holding the k-th element for both problems
         for (int q = 0; q < 2; ++q) {
             const unsigned* h = hist + ((q == 1 && !same) ? 8192 : 0);
-            const int nb = 1 << wd, per = nb / 1024 > 0 ? nb / 1024 : 1;
+            const int nb = 1 << wd, per = nb / NT > 0 ? nb / NT : 1;
             unsigned s = 0;
             for (int b = 0; b < per; ++b) { const int idx = t * per + b; if (idx < nb) s += h[idx]; }
             scan_part[t] = s;
             __syncthreads();
-            for (int o = 1; o < 1024; o <<= 1) {
+            for (int o = 1; o < NT; o <<= 1) {
                 const unsigned v = (t >= o) ? scan_part[t - o] : 0;
                 __syncthreads();
                 scan_part[t] += v;
@@ -486,8 +591,8 @@ static int sf_group_reduce(const unsigned long long* values, long long ld, const
     dim3 grid(n_groups, n_reps);
     if (want_ratio) {
         const size_t smem = 2 * 8192 * sizeof(unsigned);
-        H3D_CHECK(cudaFuncSetAttribute(median_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        median_select_kernel<<<grid, 1024, smem, st>>>(values, ld, gstart, red, valid, n_reps);
+        H3D_CHECK(cudaFuncSetAttribute(median_select_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        median_select_kernel<512><<<grid, 512, smem, st>>>(values, ld, gstart, red, valid, n_reps);
         H3D_LAUNCHED("median_select_kernel");
     } else {
         group_sum_kernel<<<grid, 1024, 0, st>>>(values, ld, gstart, red, n_reps);

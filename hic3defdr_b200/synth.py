@@ -21,6 +21,19 @@ MM10_10KB = {  # ceil(mm10 chromosome length / 10 kb)
     'chrX': 17104,
 }
 
+_HG38_BP = {  # GRCh38 primary assembly chromosome lengths (bp)
+    'chr1': 248956422, 'chr2': 242193529, 'chr3': 198295559,
+    'chr4': 190214555, 'chr5': 181538259, 'chr6': 170805979,
+    'chr7': 159345973, 'chr8': 145138636, 'chr9': 138394717,
+    'chr10': 133797422, 'chr11': 135086622, 'chr12': 133275309,
+    'chr13': 114364328, 'chr14': 107043718, 'chr15': 101991189,
+    'chr16': 90338345, 'chr17': 83257441, 'chr18': 80373285,
+    'chr19': 58617616, 'chr20': 64444167, 'chr21': 46709983,
+    'chr22': 50818468, 'chrX': 156040895,
+}
+HG38_5KB = {c: -(-n // 5000) for c, n in _HG38_BP.items()}
+HG38_CHR1_1KB = {'chr1': -(-_HG38_BP['chr1'] // 1000)}
+
 BASE_SEED = 20261018
 
 

@@ -1,0 +1,57 @@
+"""Wall-clock of the drop-in class on files (file patterns in -> .npy on disk),
+per step: SURVEY.md section 8(d) "end-to-end" clock for BASELINE configs[0]
+(chr18 + chr19, mouse-sized, 10 kb, 2-vs-2).
+
+    python tools/time_class.py [workdir] [--chroms chr18,chr19]
+"""
+import json
+import os
+import sys
+import tempfile
+import time
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+
+
+def main():
+    import torch
+    from hic3defdr_b200 import HiC3DeFDR
+    from hic3defdr_b200.synth import MM10_10KB, write_dataset
+    args = [a for a in sys.argv[1:] if not a.startswith('--')]
+    root = args[0] if args else tempfile.mkdtemp(prefix='h3d_class_')
+    chroms = ['chr18', 'chr19']
+    for a in sys.argv[1:]:
+        if a.startswith('--chroms'):
+            chroms = a.split('=', 1)[1].split(',')
+    t0 = time.perf_counter()
+    kw = write_dataset(os.path.join(root, 'in'),
+                       {c: MM10_10KB[c] for c in chroms}, n_reps=4,
+                       dist_max=200, config=1)
+    t_gen = time.perf_counter() - t0
+    out = {}
+    for trial in range(2):           # second pass: page cache and CUDA context warm
+        outdir = os.path.join(root, 'out%d' % trial)
+        h = HiC3DeFDR(outdir=outdir, dist_thresh_max=200, **kw)
+        times = {}
+        t_all = time.perf_counter()
+        for name, fn in (('prepare_data', h.prepare_data),
+                         ('estimate_disp', h.estimate_disp),
+                         ('lrt', h.lrt), ('bh', h.bh)):
+            t = time.perf_counter()
+            fn()
+            torch.cuda.synchronize()
+            times[name] = round(time.perf_counter() - t, 3)
+        times['total'] = round(time.perf_counter() - t_all, 3)
+        n_px = sum(len(h.load_data('row', c)) for c in chroms)
+        nbytes = sum(os.path.getsize(os.path.join(outdir, f))
+                     for f in os.listdir(outdir))
+        out['trial%d' % trial] = dict(times, union_pixels=n_px,
+                                      output_bytes=nbytes,
+                                      pixels_per_s=round(n_px / times['total']))
+    out['generate_inputs_s'] = round(t_gen, 1)
+    print(json.dumps(out))
+
+
+if __name__ == '__main__':
+    main()
