@@ -39,9 +39,14 @@ if REPO not in sys.path:
 from hic3defdr_b200.synth import HG38_5KB, HG38_CHR1_1KB, MM10_10KB  # noqa: E402
 
 # SURVEY.md section 8(d), cost model v1: FP64 instruction-equivalents of one
-# pixel-equalisation (fit_mu_hat 500 + gmean 85 + 2 x q2q 2150) for R_c = 2;
-# FMA = 2 flops.
-EQUALIZE_INST_EQ_PER_PX = 4885.0
+# pixel-equalisation = fit_mu_hat (8 Newton steps of 24 per replicate + 14)
+# + gmean (a log of 30 per replicate + an exp) + one q2q of 2150 per replicate
+# of the condition; 4885 for R_c = 2 (500 + 85 + 2 x 2150).  FMA = 2 flops.
+def equalize_inst_eq_per_px(reps_per_cond):
+    if reps_per_cond == 2:
+        return 4885.0
+    return 8.0 * (24.0 * reps_per_cond + 14.0) + 30.0 * reps_per_cond + 25.0 \
+        + 2150.0 * reps_per_cond
 
 WORKLOADS = {
     'mouse10kb': dict(chroms=MM10_10KB, n_reps=4, dist_max=200, amp=300.0,
@@ -262,6 +267,9 @@ def main():
     ap.add_argument('--impl', default='b200')
     ap.add_argument('--workload', default='mouse10kb')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true',
+                    help='skip the host-buffer leg (secondary workloads whose '
+                         'pinned output buffers would not fit the host)')
     ap.add_argument('--shard', default='chroms', choices=('chroms', 'rows'),
                     help='multi-GPU partition: whole chromosomes per rank, or '
                          'a row range of every chromosome per rank')
@@ -314,7 +322,8 @@ def main():
                                      int(bounds[rank + 1]))
             torch.cuda.empty_cache()
         dev_inputs.append((staging.csr_to_device(mats, n), bias))
-        host_inputs.append((HostChrom(mats, bias), n))
+        if not args.no_e2e:
+            host_inputs.append((HostChrom(mats, bias), n))
     torch.cuda.synchronize()
 
     def sync_all():
@@ -398,28 +407,35 @@ def main():
     stats = out[3]
     del out
     # ---- e2e: host buffers in, host buffers out --------------------------
-    step_e2e()
-    step_e2e()
-    trace.reset()
-    ms_e2e, out_e2e = timed(step_e2e, args.steps)
-    d2h = out_e2e[2]
-    del out_e2e
-    if rank == 0:
-        trace.report('step_e2e, rank 0, per step', args.steps)
+    ms_e2e, d2h = None, 0
+    if not args.no_e2e:
+        step_e2e()
+        step_e2e()
+        trace.reset()
+        ms_e2e, out_e2e = timed(step_e2e, args.steps)
+        d2h = out_e2e[2]
+        del out_e2e
+        if rank == 0:
+            trace.report('step_e2e, rank 0, per step', args.steps)
     sampler.stop_flag = True
     sampler.join()
     h2d = sum(h.nbytes for h, _ in host_inputs)
+    in_bytes = sum(sum(t.numel() * t.element_size()
+                       for ts in (c.indptr, c.indices, c.data) for t in ts) +
+                   b.numel() * 8 for c, b in dev_inputs)
 
-    tot = torch.tensor([n_px_local, n_d_local, h2d, d2h, launches],
+    tot = torch.tensor([n_px_local, n_d_local, h2d, d2h, launches, in_bytes],
                        dtype=torch.float64, device='cuda')
     if world > 1:
         td.all_reduce(tot)
-    n_px, n_d, h2d_all, d2h_all, launches_all = [float(v) for v in tot.cpu()]
+    n_px, n_d, h2d_all, d2h_all, launches_all, in_all = \
+        [float(v) for v in tot.cpu()]
 
     if rank == 0:
         peak = ops.fp64_peak_tflops()
         eq_s = stats['equalize_us'] * 1e-6
-        eq_flops = 2.0 * EQUALIZE_INST_EQ_PER_PX * stats['pixel_equalizations']
+        inst_eq = equalize_inst_eq_per_px(cfg['n_reps'] // 2)
+        eq_flops = 2.0 * inst_eq * stats['pixel_equalizations']
         achieved = eq_flops / eq_s / 1e12 if eq_s > 0 else None
         traffic = None
         try:
@@ -453,10 +469,10 @@ def main():
                                  'dispersion pooled by distance (all-to-all); '
                                  'BH by distributed sort/rank (all-to-all)',
                         l2='inputs (%.1f GB/step) larger than L2'
-                           % (h2d_all / 1e9)),
+                           % (in_all / 1e9)),
             e2e=dict(value=n_px / (ms_e2e / args.steps * 1e-3),
                      unit='pixels/s', h2d_bytes_per_step=int(h2d_all),
-                     d2h_bytes_per_step=int(d2h_all)),
+                     d2h_bytes_per_step=int(d2h_all)) if ms_e2e else None,
             gpu_launches=int(launches_all),
             roofline=dict(
                 bound='fp64', kernel='equalize_kernel',
@@ -467,7 +483,7 @@ def main():
                       '(SURVEY 8(d)) x %d pixel-equalisations / %.1f ms of '
                       'equalize_kernel (CUDA events, %d launches/step, rank 0); '
                       'peak = FP64 FMA rate measured in this run'
-                      % (EQUALIZE_INST_EQ_PER_PX,
+                      % (inst_eq,
                          stats['pixel_equalizations'], eq_s * 1e3,
                          stats['equalize_launches'])),
             qcml=dict(outer_iterations=stats['outer_iterations'],

@@ -24,6 +24,7 @@ Differences a caller can observe (all documented in DESIGN.md):
 import json
 import os
 import sys
+import threading
 from concurrent.futures import ThreadPoolExecutor
 
 import dill as pickle
@@ -64,6 +65,52 @@ def _loadtxt(path):
         return np.loadtxt(path)
 
 
+class _AsyncWriter(object):
+    """Background ``.npy`` writers (with the
+    arithmetic on the GPU the wall time of a run is file I/O).  ``submit``
+    returns at once; a worker thread waits for the kernels that produce the
+    tensor (CUDA event), copies it to the host on its own stream and writes the
+    file while the main thread goes on with the next chromosome.  ``wait``
+    blocks until every file is on disk and re-raises the first failure."""
+
+    def __init__(self, n_threads):
+        self.pool = ThreadPoolExecutor(max(1, n_threads))
+        self.futures = []
+        self.streams = {}
+        self.lock = threading.Lock()
+
+    def _job(self, data, path, event, device):
+        if isinstance(data, torch.Tensor):
+            if data.is_cuda:
+                torch.cuda.set_device(device)
+                key = threading.get_ident()
+                with self.lock:
+                    stream = self.streams.get(key)
+                    if stream is None:
+                        stream = self.streams[key] = torch.cuda.Stream()
+                stream.wait_event(event)
+                with torch.cuda.stream(stream):
+                    host = data.to('cpu', non_blocking=False)
+                stream.synchronize()
+                data = host
+            data = data.numpy()
+        np.save(path, data)
+
+    def submit(self, data, path):
+        event, device = None, None
+        if isinstance(data, torch.Tensor) and data.is_cuda:
+            device = data.device.index
+            event = torch.cuda.Event()
+            event.record(torch.cuda.current_stream())
+        self.futures.append(self.pool.submit(self._job, data, path, event,
+                                             device))
+
+    def wait(self):
+        futures, self.futures = self.futures, []
+        for f in futures:
+            f.result()
+
+
 class HiC3DeFDR(object):
     """See ``hic3defdr.analysis.constructor.HiC3DeFDR`` for the attributes."""
 
@@ -93,6 +140,8 @@ class HiC3DeFDR(object):
         hdist.barrier()
         self._cache = {}
         self._shards = {}
+        self._writer = None
+        self._defer_writes = False
         self.timings = {}
 
     # ---------------------------------------------------------------- core
@@ -124,6 +173,7 @@ class HiC3DeFDR(object):
     def load_data(self, name, chrom=None, idx=None, rep=None, cond=None,
                   coo=False):
         """analysis/core.py:62-195 (same semantics, numpy in / out)."""
+        self._flush_writes()
         if name == 'loop_idx' and self.loop_patterns is None and idx is None \
                 and chrom != 'all':
             disp_idx = self.load_data('disp_idx', chrom)
@@ -239,6 +289,7 @@ class HiC3DeFDR(object):
         cut evenly (the later steps accept any contiguous partition)."""
         b = self._shards.get(chrom)
         if b is None:
+            self._flush_writes()
             ws, me = hdist.world_size(), hdist.rank()
             disp_idx = np.load('%s/disp_idx_%s.npy' % (self.outdir, chrom),
                                mmap_mode='r')
@@ -289,11 +340,40 @@ class HiC3DeFDR(object):
         return n_threads
 
     def _save_many(self, items, n_threads=-1):
-        """items: list of (tensor-or-array, name, chrom)."""
-        host = [(d.cpu().numpy() if isinstance(d, torch.Tensor) else d, n, c)
-                for d, n, c in items]
+        """items: list of (tensor-or-array, name, chrom).  The files are
+        written by background threads; they are complete when the calling step
+        returns (or, inside ``run_to_qvalues``, when that returns)."""
+        if self._writer is None:
+            self._writer = _AsyncWriter(self._io_threads(n_threads))
+        for data, name, chrom in items:
+            path = '%s/%s.npy' % (self.outdir, name) if chrom is None else \
+                '%s/%s_%s.npy' % (self.outdir, name, chrom)
+            self._writer.submit(data, path)
+        if not self._defer_writes:
+            self._writer.wait()
+
+    def _flush_writes(self):
+        if self._writer is not None:
+            self._writer.wait()
+
+    def _load_inputs(self, chrom, n_threads=-1):
+        """Host side of ``prepare_data`` for one chromosome: bias vectors,
+        replicate matrices (each npz inflated once, in parallel) and loop
+        pixels.  Thread-safe: ``prepare_data()`` runs it for the next
+        chromosome while the GPU works on the current one."""
+        bias_raw = np.ascontiguousarray(np.array(
+            [_loadtxt(p.replace('<chrom>', chrom))
+             for p in self.bias_patterns]).T)
         with ThreadPoolExecutor(self._io_threads(n_threads)) as ex:
-            list(ex.map(lambda a: self.save_data(*a), host))
+            mats = list(ex.map(
+                lambda p: sparse.load_npz(p.replace('<chrom>', chrom)).tocsr(),
+                self.raw_npz_patterns))
+        loop_pixels = None
+        if self.loop_patterns:
+            loop_pixels = set().union(
+                *sum((load_clusters(pattern.replace('<chrom>', chrom))
+                      for pattern in self.loop_patterns.values()), []))
+        return bias_raw, mats, loop_pixels
 
     def _chrom_state(self, chrom, names):
         """device tensors of one chromosome, from the cache or from disk."""
@@ -301,6 +381,7 @@ class HiC3DeFDR(object):
         for name in names:
             if name in c:
                 continue
+            self._flush_writes()
             if name == 'bias':
                 self._bias_device(chrom)
             elif name == 'disp_index':
@@ -332,29 +413,43 @@ class HiC3DeFDR(object):
 
     # ------------------------------------------------------- prepare_data
     def prepare_data(self, chrom=None, norm='conditional_mor', n_bins=-1,
-                     n_threads=-1, verbose=True):
+                     n_threads=-1, verbose=True, _inputs=None):
         """analysis/analysis.py:28-133."""
         if n_bins == -1:
             n_bins = int(self.dist_thresh_max / 5)
         if norm not in ops.NORMS:
             raise KeyError(norm)
         if chrom is None:
-            for c in self._my_chroms():
-                self.prepare_data(chrom=c, norm=norm, n_bins=n_bins,
-                                  n_threads=n_threads, verbose=False)
+            # the next chromosome's files are read (npz inflate, text parse)
+            # while this one is on the GPU, and this one's outputs are written
+            # while the next one is computed
+            chroms = self._my_chroms()
+            defer, self._defer_writes = self._defer_writes, True
+            try:
+                with ThreadPoolExecutor(1) as loader:
+                    nxt = loader.submit(self._load_inputs, chroms[0],
+                                        n_threads) if chroms else None
+                    for i, c in enumerate(chroms):
+                        inputs = nxt.result()
+                        nxt = loader.submit(self._load_inputs, chroms[i + 1],
+                                            n_threads) \
+                            if i + 1 < len(chroms) else None
+                        self.prepare_data(chrom=c, norm=norm, n_bins=n_bins,
+                                          n_threads=n_threads, verbose=False,
+                                          _inputs=inputs)
+                        del inputs
+            finally:
+                self._defer_writes = defer
+            if not defer:
+                self._flush_writes()
             hdist.barrier()
             return
         eprint('preparing data for chrom %s' % chrom)
         eprint('  loading bias', skip=not verbose)
         self._cache.pop(chrom, None)
-        bias_raw = np.ascontiguousarray(np.array(
-            [_loadtxt(p.replace('<chrom>', chrom))
-             for p in self.bias_patterns]).T)
         eprint('  computing union pixel set', skip=not verbose)
-        with ThreadPoolExecutor(self._io_threads(n_threads)) as ex:
-            mats = list(ex.map(
-                lambda p: sparse.load_npz(p.replace('<chrom>', chrom)).tocsr(),
-                self.raw_npz_patterns))
+        bias_raw, mats, loop_pixels = _inputs if _inputs is not None else \
+            self._load_inputs(chrom, n_threads)
         sharded = self._row_sharded()
         if sharded:
             bounds = hdist.row_ranges(staging.row_weights(mats))
@@ -363,12 +458,8 @@ class HiC3DeFDR(object):
                                       int(bounds[me + 1]))
         csr = ops.DeviceCSR(mats)
         del mats
-        loop_pixels = None
         if self.loop_patterns:
             eprint('  making loop_idx', skip=not verbose)
-            loop_pixels = set().union(
-                *sum((load_clusters(pattern.replace('<chrom>', chrom))
-                      for pattern in self.loop_patterns.values()), []))
         eprint('  loading raw data', skip=not verbose)
         eprint('  loading balanced data', skip=not verbose)
         eprint('  computing size factors', skip=not verbose)
@@ -437,9 +528,15 @@ class HiC3DeFDR(object):
     def lrt(self, chrom=None, refit_mu=True, n_threads=-1, verbose=True):
         """analysis/analysis.py:225-284."""
         if chrom is None:
-            for c in self._my_chroms():
-                self.lrt(chrom=c, refit_mu=refit_mu, n_threads=n_threads,
-                         verbose=False)
+            defer, self._defer_writes = self._defer_writes, True
+            try:
+                for c in self._my_chroms():
+                    self.lrt(chrom=c, refit_mu=refit_mu, n_threads=n_threads,
+                             verbose=False)
+            finally:
+                self._defer_writes = defer
+            if not defer:
+                self._flush_writes()
             hdist.barrier()
             return
         eprint('running LRT for chrom %s' % chrom)
@@ -474,9 +571,19 @@ class HiC3DeFDR(object):
                        weighted_lowess=True, refit_mu=True, n_threads=-1,
                        verbose=True):
         """analysis/analysis.py:305-364."""
-        self.prepare_data(norm=norm, n_bins=n_bins_norm, n_threads=n_threads)
-        self.estimate_disp(
-            estimator=estimator, frac=frac, auto_frac_factor=auto_frac_factor,
-            weighted_lowess=weighted_lowess, n_threads=n_threads)
-        self.lrt(refit_mu=refit_mu, n_threads=n_threads)
-        self.bh()
+        # one wait for the background writers at the very end: the files of a
+        # step are written while the next step computes
+        self._defer_writes = True
+        try:
+            self.prepare_data(norm=norm, n_bins=n_bins_norm,
+                              n_threads=n_threads)
+            self.estimate_disp(
+                estimator=estimator, frac=frac,
+                auto_frac_factor=auto_frac_factor,
+                weighted_lowess=weighted_lowess, n_threads=n_threads)
+            self.lrt(refit_mu=refit_mu, n_threads=n_threads)
+            self.bh()
+        finally:
+            self._defer_writes = False
+            self._flush_writes()
+        hdist.barrier()

@@ -217,10 +217,14 @@ __global__ void rank_emit_kernel(KeyFn keys, long long n, int n_keys,
         __syncwarp();
         const long long lo = (long long)seg * seg_len;
         const long long hi = (lo + seg_len < n) ? lo + seg_len : n;
+        // the key of the next round is loaded before this round's (serial)
+        // match / count / store chain, so that the chain does not start with a
+        // global-memory latency every 32 elements
+        int k_next = (lo + lane < hi) ? keys(lo + lane) : -1;
         for (long long base = lo; base < hi; base += 32) {
             const long long i = base + lane;
-            const bool valid = i < hi;
-            int k = valid ? keys(i) : -1;
+            int k = k_next;
+            k_next = (i + 32 < hi) ? keys(i + 32) : -1;
             if (k < 0 || k >= n_keys) k = -1;
             const unsigned act = __ballot_sync(0xffffffffu, k >= 0);
             if (k >= 0) {

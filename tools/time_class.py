@@ -49,6 +49,15 @@ def main():
         out['trial%d' % trial] = dict(times, union_pixels=n_px,
                                       output_bytes=nbytes,
                                       pixels_per_s=round(n_px / times['total']))
+    # the whole pipeline in one call: writers of a step overlap the next step
+    outdir = os.path.join(root, 'out_all')
+    h = HiC3DeFDR(outdir=outdir, dist_thresh_max=200, **kw)
+    t = time.perf_counter()
+    h.run_to_qvalues()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t
+    out['run_to_qvalues'] = dict(total=round(dt, 3),
+                                 pixels_per_s=round(n_px / dt))
     out['generate_inputs_s'] = round(t_gen, 1)
     print(json.dumps(out))
 
