@@ -209,6 +209,15 @@ def all_gather_varlen(local):
 BH_SAMPLES = 4096      # splitter candidates contributed by each rank
 
 
+def sample_positions(n, take, device=None):
+    """``take`` evenly strided positions in [0, n), first and last included.
+    Integer arithmetic: a float32 ``linspace(0, n - 1, take)`` rounds n - 1 up
+    past the end once n exceeds 2^24 (a rank of the mouse genome holds 19 M
+    p-values)."""
+    return (torch.arange(take, dtype=torch.int64, device=device) *
+            (n - 1)) // max(take - 1, 1)
+
+
 def _partition(bucket, n_buckets):
     """Stable partition by bucket id: (position of every element in
     bucket-major order, bucket sizes as a host int64 array)."""
@@ -251,7 +260,7 @@ def global_bh(local_p, bh_fn=None, bh_ranked_fn=None, carry_fn=None):
                         device=device)
     if n_fin:
         take = min(BH_SAMPLES, n_fin)
-        sel = torch.linspace(0, n_fin - 1, take, device=device).long()
+        sel = sample_positions(n_fin, take, device)
         sample[:take] = fin_vals[sel]
     gathered = [torch.empty_like(sample) for _ in range(ws)]
     td.all_gather(gathered, sample)

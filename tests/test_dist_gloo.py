@@ -296,3 +296,15 @@ def test_lpt_and_ranges():
         assert (d % 8 == k).all() and (keys[d] == k * per + np.arange(len(d))).all()
     keys, per = hd.distance_keys(7, 1)
     assert per == 7 and (keys == np.arange(7)).all()
+
+
+def test_bh_sample_positions_stay_in_range():
+    """regression: float32 linspace(0, n - 1, take) indexed one past the end
+    for n > 2^24 (device-side assert in the 2-GPU row-sharded mouse run)"""
+    from hic3defdr_b200 import dist as hd
+    for n in (1, 2, 4095, 4096, 4097, 2 ** 24 + 2, 19_366_195, 38_732_388,
+              2 ** 31 - 1):
+        take = min(hd.BH_SAMPLES, n)
+        sel = hd.sample_positions(n, take).numpy()
+        assert sel[0] == 0 and sel[-1] == n - 1
+        assert (np.diff(sel) >= 0).all() and len(sel) == take
