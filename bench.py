@@ -69,6 +69,9 @@ WORKLOADS = {
     'tiny': dict(chroms={'chrA': 1500, 'chrB': 1100}, n_reps=4, dist_max=60,
                  amp=200.0, desc='tiny smoke workload'),
 }
+# chromosomes whose host -> device copies are queued ahead of the kernels
+PREFETCH_DEPTH = int(os.environ.get('H3D_PREFETCH_DEPTH', '4'))
+DRAIN_AFTER_UPLOAD = os.environ.get('H3D_DRAIN_AFTER_UPLOAD', '1') != '0'
 CPU_SAMPLE = dict(chroms={'s1': 700, 's2': 500}, dist_max=200)
 # --impl reference uses every host core: as many chromosomes as a genome has,
 # so that the reference's per-chromosome process pools are busy
@@ -256,6 +259,45 @@ def run_reference(args, cfg):
     print(json.dumps(line))
 
 
+# algorithmic bytes per union pixel of the HBM-bound
+# stages (R = 4: union + gathers 83, size factors 40, scale / filter 105; pooling
+# 16 R read + 16 R written per tested pixel; BH lower bound 16 per tested pixel)
+# and FP64 instruction-equivalents per tested pixel of the LRT (2.5 k).
+def stage_rooflines(stage_ms, n_px, n_d, n_reps, fp64_peak_tflops):
+    """Rank 0's stages of the device-resident step: CUDA-event ms per step
+    and the fraction of the roofline that bounds each (HBM 6544.7 GB/s from
+    MEASURED_PEAKS.json, FP64 as measured in this run)."""
+    hbm = 6544.7
+    try:
+        with open(os.path.join(REPO, 'MEASURED_PEAKS.json')) as h:
+            hbm = float(json.load(h)['hbm_gbs'])
+    except Exception:
+        pass
+    r4 = n_reps / 4.0
+    model = {
+        'prepare_data': ('hbm', n_px * (12 * 3.6 * r4 + 8 + 8 * n_reps    # S1
+                                        + 8 + 8 * n_reps                  # S2
+                                        + 8 + 24 * n_reps + 1)),          # S3
+        'estimate_disp/pool': ('hbm', n_d * (8 + 32 * n_reps)),
+        'lrt': ('fp64', n_d * 2500.0 * 2.0),
+        'bh': ('hbm', n_d * 16.0),
+    }
+    out = {}
+    for name, ms in stage_ms.items():
+        entry = dict(ms=round(ms, 3))
+        if name in model and ms > 0:
+            kind, work = model[name]
+            if kind == 'hbm':
+                entry.update(bound='hbm', achieved_gbs=round(work / ms / 1e6, 1),
+                             frac=round(work / ms / 1e6 / hbm, 4))
+            elif fp64_peak_tflops:
+                entry.update(bound='fp64',
+                             achieved_tflops=round(work / ms / 1e9, 2),
+                             frac=round(work / ms / 1e9 / fp64_peak_tflops, 4))
+        out[name] = entry
+    return out
+
+
 # --------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------
@@ -342,9 +384,11 @@ def main():
         # host buffers in, host buffers out: uploads run one chromosome ahead
         # of the kernels, every output drains to pinned memory as soon as it
         # is final (hic3defdr_b200/staging.py)
-        drain = staging.OutputDrain(pinned_out)
+        prefetch = staging.InputPrefetcher(host_chroms, depth=PREFETCH_DEPTH)
+        drain = staging.OutputDrain(
+            pinned_out, after=prefetch if DRAIN_AFTER_UPLOAD else None)
         states, dpd, fns, stats = engine.run_to_qvalues(
-            staging.InputPrefetcher(host_chroms), design, sink=drain, **kw)
+            prefetch, design, sink=drain, **kw)
         with trace.stage('drain_wait'):
             out = drain.wait()
         torch.cuda.synchronize()
@@ -399,7 +443,10 @@ def main():
     sampler.start()
     lib().query('h3d_reset_launch_count')
     trace.reset()
+    trace.record_events(True)       # CUDA event pairs around the stages
     ms, out = timed(step_device, args.steps)
+    stage_ms = {k: v / args.steps for k, v in trace.event_ms().items()}
+    trace.record_events(False)
     launches = int(lib().query('h3d_launch_count'))
     if rank == 0:
         trace.report('step_device, rank 0, per step', args.steps)
@@ -411,6 +458,18 @@ def main():
     if not args.no_e2e:
         step_e2e()
         step_e2e()
+        if os.environ.get('H3D_E2E_TIMELINE') and rank == 0:
+            # where the overlapped host-buffer step spends its time: CUDA event
+            # pairs around the stages on the compute stream (no synchronisation)
+            trace.record_events(True)
+            t0 = time.perf_counter()
+            step_e2e()
+            wall = 1e3 * (time.perf_counter() - t0)
+            print('[e2e timeline] wall %.1f ms; stages on the compute stream: %s'
+                  % (wall, {k: round(v, 1)
+                            for k, v in trace.event_ms().items()}),
+                  file=sys.stderr)
+            trace.record_events(False)
         trace.reset()
         ms_e2e, out_e2e = timed(step_e2e, args.steps)
         d2h = out_e2e[2]
@@ -490,6 +549,8 @@ def main():
                       nll_evaluations=stats['nll_evaluations'],
                       nll_ms=stats['nll_us'] * 1e-3,
                       equalize_ms=stats['equalize_us'] * 1e-3),
+            stages=stage_rooflines(stage_ms, n_px_local, n_d_local,
+                                   cfg['n_reps'], peak),
             cpu_baseline=cpu,
             host_ms_per_step=step_wall,
             clocks=sampler.summary())

@@ -16,10 +16,38 @@ ENABLED = os.environ.get('H3D_TRACE', '0') not in ('', '0')
 TIMES = collections.OrderedDict()
 COUNTS = collections.Counter()
 CALLS = collections.OrderedDict()      # name -> list of per-call ms
+# event mode (bench.py): a pair of CUDA events per stage on the current stream,
+# no synchronisation; ``event_ms()`` reads them after the caller synchronised
+EVENTS = None                          # None: off; else list of (name, ev0, ev1)
+
+
+def record_events(on=True):
+    global EVENTS
+    EVENTS = [] if on else None
+
+
+def event_ms():
+    """{stage: total ms} of the recorded event pairs (device time between the
+    stage's first and last enqueued work on the stream that runs the stages)."""
+    out = collections.OrderedDict()
+    for name, e0, e1 in EVENTS or []:
+        out[name] = out.get(name, 0.0) + e0.elapsed_time(e1)
+    return out
 
 
 @contextlib.contextmanager
 def stage(name):
+    if EVENTS is not None and not ENABLED:
+        import torch
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        try:
+            yield
+        finally:
+            e1.record()
+            EVENTS.append((name, e0, e1))
+        return
     if not ENABLED:
         yield
         return
