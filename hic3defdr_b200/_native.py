@@ -64,6 +64,8 @@ SIGNATURES = {
     'h3d_bh_ws_bytes': (c_sz, [c_ll]),
     'h3d_bh_ranked': (c_int, [vp, c_ll, c_ll, c_ll, vp, vp, vp, c_sz, vp]),
     'h3d_bh_apply_carry': (c_int, [vp, c_ll, c_dbl, vp]),
+    'h3d_connected_components': (c_int, [vp, vp, c_ll, vp, vp, vp, c_sz, vp]),
+    'h3d_connected_components_ws_bytes': (c_sz, [c_ll]),
 }
 
 

@@ -34,6 +34,7 @@ import scipy.sparse as sparse
 import torch
 
 from hic3defdr_b200 import dist as hdist
+from hic3defdr_b200 import clusters as hclusters
 from hic3defdr_b200 import engine, ops, staging
 
 
@@ -586,4 +587,125 @@ class HiC3DeFDR(object):
         finally:
             self._defer_writes = False
             self._flush_writes()
+        hdist.barrier()
+
+    # ------------------------------------------- threshold / classify / collect
+    @staticmethod
+    def _as_list(v):
+        return list(v) if hasattr(v, '__len__') else [v]
+
+    def _cluster_chroms(self):
+        """threshold / classify work on whole chromosomes from the files: in a
+        row-sharded run rank 0 takes them all."""
+        if self._row_sharded():
+            return list(self.chroms) if hdist.rank() == 0 else []
+        return self._my_chroms()
+
+    def _save_cluster_files(self, clusters, outfile, chrom):
+        hclusters.save_clusters(clusters, outfile)
+        if self.res is not None:
+            hclusters.clusters_to_table(clusters, chrom, self.res).to_csv(
+                outfile.replace('.json', '.tsv'), sep='\t')
+
+    def threshold(self, chrom=None, fdr=0.05, cluster_size=3, n_threads=-1):
+        """analysis/analysis.py:366-430: pixels with q < fdr ("sig") and with
+        q >= fdr ("insig") are clustered separately (4-connected components,
+        on the GPU) and clusters below ``cluster_size`` pixels dropped; writes
+        ``sig_<fdr>_<size>_<chrom>.json`` / ``insig_...json`` (+ ``.tsv`` when
+        ``res`` is set).  A list of FDRs is a sweep over each value (the
+        reference passes the whole list to the comparison, analysis.py:411-413,
+        which only works for one value)."""
+        if chrom is None:
+            for c in self._cluster_chroms():
+                self.threshold(chrom=c, fdr=fdr, cluster_size=cluster_size)
+            hdist.barrier()
+            return
+        eprint('thresholding and clustering chrom %s' % chrom)
+        row, col, qvalues = self.load_data('qvalues', chrom, coo=True)
+        r, c, q = ops.dev(row, torch.int32), ops.dev(col, torch.int32), \
+            ops.dev(qvalues, torch.float64)
+        for f in self._as_list(fdr):
+            for name, sel in (('sig', q < f), ('insig', q >= f)):
+                rs, cs = r[sel], c[sel]
+                label, size = ops.connected_components(rs, cs)
+                for s in self._as_list(cluster_size):
+                    found = ops.clusters_from_labels(rs, cs, label, size, s)
+                    self._save_cluster_files(
+                        found, '%s/%s_%g_%i_%s.json'
+                        % (self.outdir, name, f, s, chrom), chrom)
+
+    def classify(self, chrom=None, fdr=0.05, cluster_size=3, n_threads=-1):
+        """analysis/analysis.py:432-496 + util/classification.py:7-49: the
+        pixels of the significant clusters are assigned to the condition with
+        the largest ``mu_hat_alt`` and re-clustered per condition; writes
+        ``<cond>_<fdr>_<size>_<chrom>.json`` (+ ``.tsv`` when ``res`` is
+        set)."""
+        if chrom is None:
+            for c in self._cluster_chroms():
+                self.classify(chrom=c, fdr=fdr, cluster_size=cluster_size)
+            hdist.barrier()
+            return
+        eprint('classifying differential interactions on chrom %s' % chrom)
+        disp_idx = self.load_data('disp_idx', chrom)
+        loop_idx = self.load_data('loop_idx', chrom)
+        row = self.load_data('row', chrom, idx=(disp_idx, loop_idx))
+        col = self.load_data('col', chrom, idx=(disp_idx, loop_idx))
+        mu_hat_alt = self.load_data('mu_hat_alt', chrom, idx=loop_idx)
+        keys = hclusters.pixel_keys(row, col)
+        for f in self._as_list(fdr):
+            for s in self._as_list(cluster_size):
+                infile = '%s/sig_%g_%i_%s.json' % (self.outdir, f, s, chrom)
+                if not os.path.isfile(infile):
+                    self.threshold(chrom=chrom, fdr=f, cluster_size=s)
+                sig = hclusters.load_clusters(infile)
+                sig_px = np.concatenate(sig) if sig else \
+                    np.zeros((0, 2), dtype=np.int64)
+                idx = np.isin(keys, hclusters.pixel_keys(sig_px[:, 0],
+                                                         sig_px[:, 1]))
+                # np.argmax: the first condition wins a tie
+                classes = np.argmax(mu_hat_alt[idx, :], axis=1) \
+                    if idx.any() else np.zeros(0, dtype=np.int64)
+                for ci, cond in enumerate(self.design.columns):
+                    pick = classes == ci
+                    found = ops.find_clusters(row[idx][pick], col[idx][pick])
+                    self._save_cluster_files(
+                        found, '%s/%s_%g_%i_%s.json'
+                        % (self.outdir, cond, f, s, chrom), chrom)
+
+    def collect(self, fdr=0.05, cluster_size=3, n_threads=-1):
+        """analysis/analysis.py:498-574: one ``results_<fdr>_<size>.tsv`` with
+        the constitutive (insig) and per-condition clusters of every
+        chromosome."""
+        if self.res is None:
+            raise ValueError(
+                'the collect() step can only be run if the res kwarg was '
+                'passed during construction of the HiC3DeFDR object; please '
+                'run the classify() step instead or re-create the HiC3DeFDR '
+                'object (you do not need to re-run any other steps)')
+        eprint('collecting differential interactions')
+        for f in self._as_list(fdr):
+            for s in self._as_list(cluster_size):
+                pattern = '%s/<class>_%g_%i_<chrom>.tsv' % (self.outdir, f, s)
+                path = lambda cls, chrom: pattern.replace('<class>', cls) \
+                    .replace('<chrom>', chrom)
+                if not all(os.path.isfile(path('insig', c))
+                           for c in self.chroms):
+                    self.threshold(fdr=f, cluster_size=s)
+                if not all(os.path.isfile(path(cond, c))
+                           for cond in self.design.columns
+                           for c in self.chroms):
+                    self.classify(fdr=f, cluster_size=s)
+                if hdist.rank() != 0:
+                    continue
+                tables = []
+                for chrom in self.chroms:
+                    df = hclusters.load_cluster_table(path('insig', chrom))
+                    df['classification'] = 'constitutive'
+                    tables.append(df)
+                    for cond in self.design.columns:
+                        df = hclusters.load_cluster_table(path(cond, chrom))
+                        df['classification'] = cond
+                        tables.append(df)
+                hclusters.sort_cluster_table(pd.concat(tables)).to_csv(
+                    '%s/results_%g_%i.tsv' % (self.outdir, f, s), sep='\t')
         hdist.barrier()

@@ -635,3 +635,52 @@ def apply_bh_carry(q, carry):
     lib().call('h3d_bh_apply_carry', ptr(q), q.numel(), float(carry),
                _stream())
     return q
+
+
+# --------------------------------------------------------------------------
+# threshold / classify
+# --------------------------------------------------------------------------
+
+def connected_components(row, col):
+    """4-connected components of the pixels (row, col), which must be sorted
+    by (row, col) and unique (hic3defdr/util/clusters.py:69-96, find_clusters
+    with connectivity 1).  Returns (label, size) int32 CUDA tensors: label[i]
+    is the position of the first pixel of pixel i's component, size[i] the
+    component's pixel count at its first pixel and 0 elsewhere."""
+    r = dev(row, torch.int32)
+    c = dev(col, torch.int32)
+    n = r.numel()
+    label = torch.empty(n, dtype=torch.int32, device='cuda')
+    size = torch.empty(n, dtype=torch.int32, device='cuda')
+    if n == 0:
+        return label, size
+    wsb = lib().query('h3d_connected_components_ws_bytes', n)
+    ws = workspace(wsb)
+    lib().call('h3d_connected_components', ptr(r), ptr(c), n, ptr(label),
+               ptr(size), ptr(ws), wsb, _stream())
+    return label, size
+
+
+def clusters_from_labels(row, col, label, size, min_size=1):
+    """The components of ``connected_components`` with at least ``min_size``
+    pixels (util/thresholding.py:47-61 size_filter) as a list of (k, 2) int
+    arrays of [row, col] pairs, ordered by their first pixel."""
+    if row.numel() == 0:
+        return []
+    keep = size[label.long()] >= int(min_size)
+    lab = label[keep].cpu().numpy()
+    px = torch.stack([row[keep], col[keep]], dim=1).cpu().numpy()
+    if len(lab) == 0:
+        return []
+    order = np.argsort(lab, kind='stable')
+    lab, px = lab[order], px[order]
+    return np.split(px, np.flatnonzero(np.diff(lab)) + 1)
+
+
+def find_clusters(row, col, min_size=1):
+    """hic3defdr/util/clusters.py:69-96 (connectivity 1) on pixels sorted by
+    (row, col): list of (k, 2) int arrays of [row, col] pairs."""
+    r = dev(row, torch.int32)
+    c = dev(col, torch.int32)
+    label, size = connected_components(r, c)
+    return clusters_from_labels(r, c, label, size, min_size)

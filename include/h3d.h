@@ -289,6 +289,18 @@ int h3d_bh_ranked(const double* p, long long n, long long rank_offset, long long
                   h3d_stream_t stream);
 int h3d_bh_apply_carry(double* q, long long n, double carry, h3d_stream_t stream);
 
+/* ---- threshold / classify (the step after bh) ------------------------------ */
+
+/* find_clusters with connectivity 1, hic3defdr/util/clusters.py:69-96 (called
+ * from util/thresholding.py:7-44 and util/classification.py:7-49): the
+ * 4-connected components of a set of n pixels given sorted by (row, col),
+ * unique.  label[i] = position of the first pixel (in that order) of the
+ * component of pixel i; size[i] = number of pixels of the component whose first
+ * pixel is i, 0 for every other i.  Synchronises (input order is checked). */
+int h3d_connected_components(const int* row, const int* col, long long n, int* label,
+                             int* size, void* ws, size_t ws_bytes, h3d_stream_t stream);
+size_t h3d_connected_components_ws_bytes(long long n);
+
 #ifdef __cplusplus
 }
 #endif
