@@ -38,6 +38,19 @@ def main():
     bal = torch.rand((n_chr, 4), generator=g, device='cuda', dtype=torch.float64) * 50
     out['size_factor_table_2.4M_ms'] = timeit(
         lambda: ops.size_factor_table(bal, dist, 200, 40, 'conditional_mor'), 20)
+    # connected components (threshold()): every tested pixel of the genome as
+    # ONE set, 55 % of a 200-bin band (the reference's find_clusters walks the
+    # pixels in a Python loop: 31 k pixels/s on this container's CPU)
+    n_rows = n_big // 110
+    i = torch.arange(n_rows, device='cuda').repeat_interleave(201)
+    j = i + torch.arange(201, device='cuda').repeat(n_rows)
+    keep = torch.rand(i.numel(), generator=g, device='cuda') < 0.55
+    i, j = i[keep].to(torch.int32), j[keep].to(torch.int32)
+    ms = timeit(lambda: ops.connected_components(i, j), 3)
+    out['connected_components_%.1fM_ms' % (i.numel() / 1e6)] = ms
+    out['connected_components_Mpx_per_s'] = round(i.numel() / ms / 1e3, 1)
+    out['connected_components_gbs_of_24B_per_px'] = round(
+        24.0 * i.numel() / ms / 1e6, 1)
     print(json.dumps(out))
 
 
