@@ -84,6 +84,38 @@ constexpr int kEqTasks = H3D_EQ_TASKS;      // task slots per batch (28 B of sha
 
 struct EqTask { double x, mu_in, mu_out; };
 
+// Task order inside a batch.  0: two lists (continued-fraction tasks from the
+// front, series tasks from the back).  N > 0: each of the two lists is further
+// ordered by the predicted trip count of its incomplete-gamma loop, in N cost
+// buckets of a quarter octave each (counting sort through shared-memory
+// counters), so that the 32 tasks a warp runs together have similar lengths
+// (A/B on B200, mouse genome: 84.9 -> 81.5 ms per step; 2 or 6 buckets per octave
+// are within 1 %, 8 are slower).  Also measured and rejected: splitting the
+// quantile map after the first evaluation of its inverse and running the ~40 %
+// of the tasks that need another one as a compacted second pass -- the resumable
+// form of the Halley loop costs more (spills) than the idle lanes it saves.
+#ifndef H3D_EQ_BUCKETS
+#define H3D_EQ_BUCKETS 48
+#endif
+constexpr int kEqNB = H3D_EQ_BUCKETS > 0 ? H3D_EQ_BUCKETS : 1;
+#ifndef H3D_EQ_BUCKET_SCALE
+#define H3D_EQ_BUCKET_SCALE 4.0f            // buckets per octave of predicted trip count
+#endif
+
+// predicted iterations of the series / continued fraction at (a, x), FP32, only
+// a scheduling hint.  Both grow like sqrt(x) and shrink with the distance from
+// the mode in units of sqrt(x): the series needs n terms with
+// n^2 + 2 n (a - x) = 72 x (terms below 2^-52 of the sum), four per iteration.
+__device__ __forceinline__ int eq_cost_bucket(float a, float x, bool series) {
+    const float sx = sqrtf(fmaxf(x, 0.25f));
+    const float z = (a - x) / sx;
+    float pred;
+    if (series) pred = 1.0f + 0.25f * sx * (sqrtf(z * z + 72.0f) - z);
+    else pred = 1.0f + sx * (1.0f - 0.14f * fminf(fmaxf(-z, 0.0f), 4.0f));
+    int b = (int)(__log2f(pred) * H3D_EQ_BUCKET_SCALE);
+    return b < 0 ? 0 : (b >= kEqNB ? kEqNB - 1 : b);
+}
+
 // 4 resident CTAs per SM (<= 64 registers, a few spilled words) beat 3 without
 // spills by 18 %: the kernel waits on dependent FP64 latency, and 32 warps hide
 // more of it than 24 (A/B on B200: 105 -> 87 ms per step; 5 CTAs: 92 ms).
@@ -100,6 +132,10 @@ equalize_kernel(const double* __restrict__ x, const double* __restrict__ f, long
     EqTask* task = (EqTask*)eq_smem;
     int* task_dest = (int*)(eq_smem + (size_t)kEqTasks * sizeof(EqTask));
     __shared__ int n_right, n_left;
+#if H3D_EQ_BUCKETS
+    __shared__ int bucket_cnt[2 * kEqNB];       // [continued fraction | series] x cost bucket
+    __shared__ int bucket_base[2 * kEqNB + 1];
+#endif
     const int c = blockIdx.y;
     const int s = chunk_seg[blockIdx.x];
     const Problem& q = prob[s * cr.n_conds + c];
@@ -113,8 +149,15 @@ equalize_kernel(const double* __restrict__ x, const double* __restrict__ f, long
     const unsigned lt_mask = (1u << lane) - 1u;
     double* __restrict__ out_base = pseudo + (long long)cr.pseudo_row[c] * ld;
     constexpr int kBatchPx = kEqTasks / MAXRC;
+    static_assert(H3D_EQ_BUCKETS == 0 || kBatchPx <= 256, "one pixel per thread and batch");
     for (long long b0 = lo; b0 < hi; b0 += kBatchPx) {
         if (threadIdx.x == 0) { n_right = 0; n_left = 0; }
+#if H3D_EQ_BUCKETS
+        for (int b = threadIdx.x; b < 2 * kEqNB; b += 256) bucket_cnt[b] = 0;
+        int code[MAXRC];                        // (list << 16) | position inside the list, -1: no task
+#pragma unroll
+        for (int k = 0; k < MAXRC; ++k) code[k] = -1;
+#endif
         __syncthreads();
         const long long b1 = (b0 + kBatchPx < hi) ? b0 + kBatchPx : hi;
         for (long long i0 = b0; i0 < b1; i0 += 256) {
@@ -164,6 +207,21 @@ equalize_kernel(const double* __restrict__ x, const double* __restrict__ f, long
                     const float rin_f = 1.0f + (float)alpha * (float)mu_in;
                     const bool front = !gamma_use_series((double)((float)mu_in / rin_f),
                                                          (double)((float)xr[k] / rin_f));
+#if H3D_EQ_BUCKETS
+                    if (push) {
+                        // the slot is the task's own (replicate, pixel) position; its
+                        // place in the processing order is settled after the batch's
+                        // counters are complete
+                        const int list = (front ? 0 : kEqNB) +
+                                         eq_cost_bucket((float)mu_in / rin_f, (float)xr[k] / rin_f, !front);
+                        code[k] = (list << 16) | atomicAdd(&bucket_cnt[list], 1);
+                        const int slot = k * kBatchPx + (int)(i - b0);
+                        task[slot].x = xr[k];
+                        task[slot].mu_in = mu_in;
+                        task[slot].mu_out = mu_out;
+                    }
+                    continue;
+#endif
                     const unsigned m_r = __ballot_sync(0xffffffffu, push && front);
                     const unsigned m_l = __ballot_sync(0xffffffffu, push && !front);
                     int base_r = 0, base_l = 0;
@@ -186,6 +244,57 @@ equalize_kernel(const double* __restrict__ x, const double* __restrict__ f, long
         }
         __syncthreads();
         if (estimator == H3D_EST_CML) continue;
+#if H3D_EQ_BUCKETS
+        if (threadIdx.x < 32) {
+            // exclusive scan of the 2 * kEqNB counters by warp 0: each lane owns a
+            // contiguous run of them
+            constexpr int kPer = (2 * kEqNB + 31) / 32;
+            int own[kPer];
+            int sum = 0;
+#pragma unroll
+            for (int j = 0; j < kPer; ++j) {
+                const int b = (int)threadIdx.x * kPer + j;
+                own[j] = (b < 2 * kEqNB) ? bucket_cnt[b] : 0;
+                sum += own[j];
+            }
+            int incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((int)threadIdx.x >= o) incl += v;
+            }
+            int run = incl - sum;
+#pragma unroll
+            for (int j = 0; j < kPer; ++j) {
+                const int b = (int)threadIdx.x * kPer + j;
+                if (b < 2 * kEqNB) bucket_base[b] = run;
+                run += own[j];
+            }
+            if (threadIdx.x == 31) bucket_base[2 * kEqNB] = incl;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < MAXRC; ++k)
+            if (code[k] >= 0)
+                task_dest[bucket_base[code[k] >> 16] + (code[k] & 0xffff)] =
+                    k * kBatchPx + (int)threadIdx.x;
+        __syncthreads();
+        {
+            const int n_tasks = bucket_base[2 * kEqNB];
+            for (int t0 = 0; t0 < n_tasks; t0 += 256) {
+                const int t = t0 + threadIdx.x;
+                if (t < n_tasks) {
+                    const int slot = task_dest[t];
+                    const EqTask tk = task[slot];
+                    const int k = slot / kBatchPx;
+                    const long long i = b0 + (slot - k * kBatchPx);
+                    out_base[(long long)k * ld + i] = q2q_one(tk.x, tk.mu_in, tk.mu_out, alpha);
+                }
+            }
+        }
+        __syncthreads();
+        continue;
+#endif
         const int nR = n_right, nL = n_left;
         // continued-fraction tasks [0, nR), then series tasks [kEqTasks - nL, kEqTasks)
         for (int t0 = 0; t0 < nR + nL; t0 += 256) {
