@@ -139,8 +139,14 @@ lrt_kernel(const double* __restrict__ raw, const double* __restrict__ f,
     if (st) atomicAdd(n_failed, 1);
 }
 
+// 8 resident CTAs per SM (64 registers, ~200 bytes of spills) against 5 at 88
+// registers: 8.15 -> 7.46 ms per step (profiles/r01g: 30 % of the warp slots were
+// in use, FP64 pipe active 32 %)
+#ifndef H3D_LRT_MIN_BLOCKS
+#define H3D_LRT_MIN_BLOCKS 8
+#endif
 template <int MAXR>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, H3D_LRT_MIN_BLOCKS)
 lrt_fused_kernel(const int* __restrict__ row, const int* __restrict__ col,
                  const int* __restrict__ index, long long n_sel,
                  const long long* __restrict__ raw, const double* __restrict__ sf,
