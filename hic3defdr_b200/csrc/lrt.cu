@@ -56,6 +56,23 @@ fit_mu_kernel(const double* __restrict__ x, const double* __restrict__ b,
 
 // Shared body of the two LRT kernels: everything after the per-replicate
 // inputs (counts x, factors f, per-condition dispersions) are in registers.
+// one out-of-line copy of the Newton fit per kernel instead of one per call
+// site (null model + the loop over conditions): the straight-line code of the
+// fused kernel otherwise outgrows the instruction cache (profiles/r01g:
+// no_instruction 2.5 stalls per issue)
+#ifndef H3D_LRT_NOINLINE_FIT
+#define H3D_LRT_NOINLINE_FIT 0
+#endif
+template <int MAXR>
+#if H3D_LRT_NOINLINE_FIT
+__device__ __noinline__
+#else
+__device__ __forceinline__
+#endif
+double lrt_fit_mu(const double* xr, const double* fr, const double* ar, unsigned mask, int* st) {
+    return fit_mu<MAXR>(xr, fr, ar, mask, st);
+}
+
 template <int MAXR>
 __device__ __forceinline__ void lrt_pixel(const double* xr, const double* fr,
                                           const double* dc, const DesignMasks& dm,
@@ -73,10 +90,10 @@ __device__ __forceinline__ void lrt_pixel(const double* xr, const double* fr,
     double mu0, mu1[H3D_MAX_CONDS];
     int st = 0;
     if (refit_mu) {
-        mu0 = fit_mu<MAXR>(xr, fr, ar, dm.all_mask, &st);
+        mu0 = lrt_fit_mu<MAXR>(xr, fr, ar, dm.all_mask, &st);
         for (int c = 0; c < dm.n_conds; ++c) {
             int s2 = 0;
-            mu1[c] = fit_mu<MAXR>(xr, fr, ar, dm.cond_mask[c], &s2);
+            mu1[c] = lrt_fit_mu<MAXR>(xr, fr, ar, dm.cond_mask[c], &s2);
             st |= s2;
         }
     } else {
