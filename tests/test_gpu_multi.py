@@ -203,12 +203,12 @@ def test_two_rank_row_sharded_matches_single_process(tmp_path):
                                    rtol=1e-12, atol=0)
 
 
-def _class_worker(rank, world, port, kw, outdir):
+def _class_worker(rank, world, port, kw, outdir, shard='rows'):
     import torch
     import torch.distributed as td
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
-    os.environ['H3D_SHARD'] = 'rows'
+    os.environ['H3D_SHARD'] = shard
     torch.cuda.set_device(rank)
     td.init_process_group('nccl', rank=rank, world_size=world,
                           device_id=torch.device('cuda', rank))
@@ -278,3 +278,49 @@ def test_two_rank_row_sharded_class_writes_the_same_files(tmp_path):
         disp = ld(out2, 'disp', c)
         for dd in np.unique(d)[:10]:
             assert len(np.unique(disp[d == dd], axis=0)) == 1
+
+
+def test_two_rank_chromosome_sharded_class_writes_the_same_files(tmp_path):
+    """The drop-in class in its default multi-GPU mode (whole chromosomes per
+    rank, background writers, one barrier at the end of run_to_qvalues): the
+    files of both ranks together are the single-process files."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 CUDA devices')
+    import torch.multiprocessing as mp
+    from hic3defdr_b200 import HiC3DeFDR
+    from hic3defdr_b200.synth import write_dataset
+    root = str(tmp_path)
+    kw = write_dataset(os.path.join(root, 'in'),
+                       {'cA': 700, 'cB': 500, 'cC': 400}, n_reps=4,
+                       dist_max=DIST_MAX, amp=250.0, loops=True)
+    out1, out2 = os.path.join(root, 'one'), os.path.join(root, 'two')
+    h = HiC3DeFDR(outdir=out1, dist_thresh_max=DIST_MAX, **kw)
+    h.run_to_qvalues(n_threads=0)
+    mp.spawn(_class_worker, args=(2, _free_port(), kw, out2, 'chroms'),
+             nprocs=2, join=True)
+    ld = lambda out, k, c: np.load(os.path.join(out, '%s_%s.npy' % (k, c)))
+    for c in kw['chroms']:
+        for k in ('row', 'col', 'raw', 'disp_idx', 'loop_idx', 'size_factors',
+                  'scaled'):
+            np.testing.assert_array_equal(ld(out1, k, c), ld(out2, k, c),
+                                          err_msg=k)
+        for k in ('disp', 'pvalues', 'llr', 'mu_hat_null', 'mu_hat_alt',
+                  'qvalues'):
+            assert ld(out1, k, c).shape == ld(out2, k, c).shape, k
+    a = np.load(os.path.join(out1, 'disp_per_dist.npy'))
+    b = np.load(os.path.join(out2, 'disp_per_dist.npy'))
+    ok = np.isfinite(a)
+    assert np.array_equal(ok, np.isfinite(b))
+    np.testing.assert_allclose(a[ok], b[ok], rtol=1e-6, atol=1e-7)
+    # stage-isolated after the trend fit, as above
+    later = ('pvalues', 'llr', 'mu_hat_null', 'mu_hat_alt', 'qvalues')
+    want = {(k, c): ld(out2, k, c) for c in kw['chroms'] for k in later}
+    h3 = HiC3DeFDR.load(out2)
+    h3.lrt(n_threads=0)
+    h3.bh()
+    for (k, c), b in want.items():
+        if k == 'qvalues':
+            np.testing.assert_allclose(ld(out2, k, c), b, rtol=1e-12, atol=0)
+        else:
+            np.testing.assert_array_equal(ld(out2, k, c), b, err_msg=k)
