@@ -10,6 +10,8 @@ row, col, raw, size_factors, scaled, disp_idx (+ disp_index, the positions of
 the True entries), bias, [loop_idx], disp, pvalues, llr, mu_hat_null,
 mu_hat_alt, qvalues.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -117,7 +119,7 @@ def prepare_chrom_sharded(csr, bias_raw, design, dist_min=4, dist_max=200,
 _PREPARE_STREAMS = {}
 
 
-def prepare_many(chrom_inputs, design, n_streams=4, sink=None, **kw):
+def prepare_many(chrom_inputs, design, n_streams=None, sink=None, **kw):
     """``prepare_chrom`` over an iterable of (csr, bias_raw), up to
     ``n_streams`` chromosomes in flight, one CUDA stream each: a chromosome is
     ~25 short kernels, several of them latency-bound (rank scan, median
@@ -125,6 +127,8 @@ def prepare_many(chrom_inputs, design, n_streams=4, sink=None, **kw):
     identical to the sequential loop (each chromosome's kernels keep their
     order on their own stream).  ``sink(i, name, tensor)`` as in
     ``run_to_qvalues``."""
+    if n_streams is None:
+        n_streams = int(os.environ.get('H3D_PREPARE_STREAMS', '4'))
     main = torch.cuda.current_stream()
     dev_i = torch.cuda.current_device()
     streams = _PREPARE_STREAMS.setdefault(dev_i, [])
