@@ -507,7 +507,7 @@ def main():
         except Exception:
             pass
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:     # reported at N = 1 only
             n_cpu, dt_cpu = time_oracle(0)
             cpu = dict(value=n_cpu / dt_cpu, unit='pixels/s', cores=1,
                        kind='port', sample=sample_desc())
