@@ -282,6 +282,10 @@ def stage_rooflines(stage_ms, n_px, n_d, n_reps, fp64_peak_tflops):
         'lrt': ('fp64', n_d * 2500.0 * 2.0),
         'bh': ('hbm', n_d * 16.0),
     }
+    # DRAM bytes the BH kernels actually move per tested pixel (ncu, profiles/
+    # r01g_launches_step_device.csv: 17.2 GB for 38.7 M pixels): the sort's own
+    # efficiency, next to the 16 B/px lower bound no sort can reach
+    moved = {'bh': n_d * 444.0}
     out = {}
     for name, ms in stage_ms.items():
         entry = dict(ms=round(ms, 3))
@@ -290,6 +294,9 @@ def stage_rooflines(stage_ms, n_px, n_d, n_reps, fp64_peak_tflops):
             if kind == 'hbm':
                 entry.update(bound='hbm', achieved_gbs=round(work / ms / 1e6, 1),
                              frac=round(work / ms / 1e6 / hbm, 4))
+                if name in moved:
+                    entry.update(moved_gbs=round(moved[name] / ms / 1e6, 1),
+                                 frac_of_moved=round(moved[name] / ms / 1e6 / hbm, 4))
             elif fp64_peak_tflops:
                 entry.update(bound='fp64',
                              achieved_tflops=round(work / ms / 1e9, 2),
