@@ -84,13 +84,23 @@ def row_ranges(weight_per_row, n_ranks=None):
     return np.concatenate([[0], np.minimum(cuts, n), [n]]).astype(np.int64)
 
 
+def _all_gather_flat(t):
+    """every rank's tensor ``t`` (same shape everywhere) stacked along a new
+    first dimension: one collective into one flat buffer (the layout both the
+    NCCL and the gloo backend accept)"""
+    ws = world_size()
+    out = torch.empty(ws * t.numel(), dtype=t.dtype, device=t.device)
+    td.all_gather_into_tensor(out, t.contiguous().view(-1))
+    return out.view((ws,) + tuple(t.shape))
+
+
 def _all_gather_counts(local_counts):
+    """(world_size, len(local_counts)) int64 table of every rank's counts: one
+    collective into one tensor, one device -> host copy."""
     t = torch.from_numpy(np.ascontiguousarray(local_counts, dtype=np.int64))
     if td.get_backend() == 'nccl':
         t = t.cuda()
-    out = [torch.empty_like(t) for _ in range(world_size())]
-    td.all_gather(out, t)
-    return np.stack([o.cpu().numpy() for o in out])
+    return _all_gather_flat(t).cpu().numpy()
 
 
 def regroup_positions(recv_counts, device):
@@ -167,9 +177,9 @@ def exchange_by_distance(x, f, seg_start, n_local):
         w.wait()
     xo = torch.empty_like(xr)
     fo = torch.empty_like(fr)
-    if n_recv:
-        xo[:, pos] = xr[:, :n_recv]
-        fo[:, pos] = fr[:, :n_recv]
+    if n_recv:                  # pos is a permutation: a plain indexed copy
+        xo.index_copy_(1, pos, xr[:, :n_recv])
+        fo.index_copy_(1, pos, fr[:, :n_recv])
     seg = np.concatenate([[0], np.cumsum(recv_counts.sum(axis=0))]) \
         .astype(np.int64)
     return xo, fo, seg
@@ -185,12 +195,11 @@ def merge_disp_per_dist(disp_owned, n_dist):
     t = torch.from_numpy(np.ascontiguousarray(disp_owned))
     if td.get_backend() == 'nccl':
         t = t.cuda()
-    out = [torch.empty_like(t) for _ in range(ws)]
-    td.all_gather(out, t)
+    out = _all_gather_flat(t).cpu().numpy()
     full = np.full((n_dist, n_conds), np.nan)
     for k in range(ws):
         d = owned_distances(n_dist, k, ws)
-        full[d] = out[k].cpu().numpy()[:len(d)]
+        full[d] = out[k][:len(d)]
     return full
 
 
@@ -287,10 +296,8 @@ def global_bh(local_p, bh_fn=None, bh_ranked_fn=None, carry_fn=None):
     # lower buckets are counts of finite values
     rank_offset = int(counts[:, :me].sum())
     q_bucket, bmin = bh_ranked_fn(recv, rank_offset, n_total)
-    mins = [torch.empty_like(bmin) for _ in range(ws)]
-    td.all_gather(mins, bmin)
-    higher = [float(m.item()) for m in mins[me + 1:]]
-    carry = min(higher) if higher else float('inf')
+    higher = _all_gather_flat(bmin).cpu().numpy().ravel()[me + 1:]
+    carry = float(higher.min()) if len(higher) else float('inf')
     q_bucket = carry_fn(q_bucket, carry)
     back = torch.empty_like(send)
     td.all_to_all_single(back, q_bucket, output_split_sizes=send_splits,
@@ -368,7 +375,7 @@ def sharded_size_factor_table(balanced, dist, dist_max, n_bins, norm,
         w.wait()
     grouped = torch.empty_like(recv)
     if n_recv:
-        grouped[:, pos] = recv[:, :n_recv]
+        grouped.index_copy_(1, pos, recv[:, :n_recv])
     own_start = np.concatenate([[0], np.cumsum(recv_counts.sum(axis=0))]) \
         .astype(np.int64)
     # 4. exact medians (sums) of the owned bins, shared with every rank
