@@ -201,3 +201,27 @@ def test_load_data_semantics(run):
     assert len(r) == len(q)
     a1 = h.load_data('raw', c, rep='A1')
     assert a1.ndim == 1
+
+
+def test_threshold_and_classify_on_the_run(run):
+    """the steps after bh() on the files of the same run: every pixel with
+    q < fdr is in exactly one 'sig' cluster, every other tested loop pixel in
+    an 'insig' one, and the classified clusters partition the sig pixels"""
+    from hic3defdr_b200 import clusters as hc
+    gold, h, outdir = run
+    h.threshold(fdr=0.5, cluster_size=1)
+    h.classify(fdr=0.5, cluster_size=1)
+    for c in gold['chroms']:
+        row, col, q = h.load_data('qvalues', c, coo=True)
+        sig = hc.load_clusters(os.path.join(outdir, 'sig_0.5_1_%s.json' % c))
+        insig = hc.load_clusters(os.path.join(outdir,
+                                              'insig_0.5_1_%s.json' % c))
+        px = lambda cl: sorted(map(tuple, np.concatenate(cl).tolist())) \
+            if cl else []
+        assert px(sig) == sorted(zip(row[q < 0.5].tolist(),
+                                     col[q < 0.5].tolist()))
+        assert px(insig) == sorted(zip(row[q >= 0.5].tolist(),
+                                       col[q >= 0.5].tolist()))
+        classed = [hc.load_clusters(os.path.join(
+            outdir, '%s_0.5_1_%s.json' % (cond, c))) for cond in ('A', 'B')]
+        assert sorted(px(classed[0]) + px(classed[1])) == px(sig)
