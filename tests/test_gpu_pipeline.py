@@ -8,7 +8,7 @@ import pandas as pd
 import pytest
 import scipy.sparse as sparse
 
-from tests.helpers import load_pipeline_golden
+from tests.helpers import check_pvalues, load_pipeline_golden
 
 pytestmark = pytest.mark.gpu
 
@@ -134,7 +134,7 @@ def test_stage_chain_against_oracle(run):
         np.testing.assert_allclose(ld('mu_hat_alt'), mu1, rtol=1e-9)
         np.testing.assert_allclose(ld('llr'), llr, rtol=0, atol=1e-10)
         good = -2 * llr >= 1e-8
-        np.testing.assert_allclose(ld('pvalues')[good], p[good], rtol=1e-9)
+        check_pvalues(ld('pvalues'), ld('llr'), p, llr, good, 1)
         all_p.append(ld('pvalues')[g['loop_idx_%s' % c]])
     q = op.bh(np.concatenate(all_p))
     got_q = np.concatenate([np.load(os.path.join(outdir, 'qvalues_%s.npy' % c))

@@ -67,10 +67,11 @@ def test_incomplete_gamma_inverse(L, upper):
     L.hc_gamma_inv(P(a), P(t), n, upper, P(y))
     yr = sp.gammainccinv(a, t) if upper else sp.gammaincinv(a, t)
     m = np.isfinite(yr) & (yr > 1e-290)
-    # the Halley iteration stops after a step below 2e-4 distribution widths
-    # (error left ~ step^3); measured 1.8e-12 from the crude start y = a used
-    # here, 4e-13 from the Wilson-Hilferty start q2q uses
-    assert (np.abs(y[m] - yr[m]) / yr[m]).max() < 5e-12
+    # the Halley iteration stops after a step below 1e-3 distribution widths
+    # (error left ~ step^3; h3d_math.cuh lists accuracy against tolerance):
+    # measured 1.7e-10 from the crude start y = a used here, 4.5e-11 through
+    # q2q, which starts from the Wilson-Hilferty map (test_q2q_vs_oracle)
+    assert (np.abs(y[m] - yr[m]) / yr[m]).max() < 5e-10
 
 
 @pytest.mark.parametrize('alpha', [0.01, 0.0005, 0.3])
@@ -88,8 +89,10 @@ def test_q2q_vs_oracle(L, alpha):
     L.hc_q2q(P(x), P(mi), P(mo), ctypes.c_double(alpha), n, P(out))
     assert np.array_equal(np.isfinite(out), np.isfinite(ref))
     m = np.isfinite(ref)
-    # relative to max(value, 1e-3): tiny outputs are cancellation residues
-    assert (np.abs(out[m] - ref[m]) / np.maximum(ref[m], 1e-3)).max() < 1e-11
+    # relative to max(value, 1e-3): tiny outputs are cancellation residues;
+    # 4.5e-11 at the Halley stopping tolerance of 1e-3 (h3d_math.cuh), 20x
+    # inside the 1e-9 budget of the dispersions the pseudo-data feed
+    assert (np.abs(out[m] - ref[m]) / np.maximum(ref[m], 1e-3)).max() < 1e-10
 
 
 def test_fit_mu_vs_oracle(L):
