@@ -219,7 +219,11 @@ H3D_HD double fit_mu(const double* x, const double* b, const double* alpha,
             continue;
         }
         if (!(nxt > mu)) return mu;          // monotone sequence hit round-off
-        const bool done = (nxt - mu) <= 4.0 * kEps * nxt;
+        // quadratic convergence from the left: the step just taken is (to first
+        // order) the error of mu, the error of nxt is ~ K step^2 / nxt with
+        // K = a mu / (1 + a mu) < 1 -- a relative step below 1e-8 leaves nxt
+        // converged to round-off, and one Newton sweep of five is saved
+        const bool done = (nxt - mu) <= 1e-8 * nxt;
         mu = nxt;
         if (done) return mu;
     }
