@@ -17,11 +17,11 @@ chr1-19,X at 10 kb, 2-vs-2 replicates, default filtering).
   roofline  the dominant kernel (equalize_kernel, FP64-pipe bound): model FP64
             flops / its CUDA-event time, against the FP64 FMA rate measured in
             this run (MEASURED_PEAKS.json has no FP64 entry)
-  cpu_baseline  the oracle port timed on one host core on a bounded sample of
-            the same workload
---impl reference: the oracle port with all host threads (the reference is pure
-Python and cannot be installed on the GPU box; oracle/ is its restatement,
-pinned bitwise to it by tests/golden).
+  cpu_baseline  the UNMODIFIED reference (oracle/_ref copy of the pure-Python
+            package, made by __graft_entry__.build()) timed with all host cores
+            on a bounded sample of the same workload
+--impl reference: the same, K steps sized to a few minutes in total; when the
+budget allows (few steps) the sample is BASELINE configs[0] at full size.
 """
 import argparse
 import json
@@ -72,11 +72,6 @@ WORKLOADS = {
 # chromosomes whose host -> device copies are queued ahead of the kernels
 PREFETCH_DEPTH = int(os.environ.get('H3D_PREFETCH_DEPTH', '4'))
 DRAIN_AFTER_UPLOAD = os.environ.get('H3D_DRAIN_AFTER_UPLOAD', '1') != '0'
-CPU_SAMPLE = dict(chroms={'s1': 700, 's2': 500}, dist_max=200)
-# --impl reference uses every host core: as many chromosomes as a genome has,
-# so that the reference's per-chromosome process pools are busy
-REF_SAMPLE = dict(chroms={'s%d' % i: 520 + 10 * i for i in range(20)},
-                  dist_max=200)
 
 
 # --------------------------------------------------------------------------
@@ -199,60 +194,70 @@ class ClockSampler(threading.Thread):
 
 
 # --------------------------------------------------------------------------
-# reference arm / cpu baseline (oracle port on host cores)
+# reference arm / cpu baseline: the UNMODIFIED reference on host cores
+# (oracle/reference_bench.py -> oracle/refrun.py; /root/reference in the build
+# container, the copy under oracle/_ref on the GPU box)
 # --------------------------------------------------------------------------
-def cpu_inputs(sample):
-    from hic3defdr_b200.synth import make_chrom
-    ins = []
-    for i, (c, n) in enumerate(sample['chroms'].items()):
-        mats, bias, _ = make_chrom(n, 4, sample['dist_max'],
-                                   seed=20261018 + 2000 + 100 * i, amp=300.0)
-        ins.append((mats, bias))
-    return ins
+CPU_BASELINE_BINS = 1800          # ~0.36 M union pixels: 10-30 s of CPU work
+REF_BUDGET_S = 240.0              # whole --impl reference run, all K steps
 
 
-def time_oracle(n_threads, sample=CPU_SAMPLE, ins=None):
-    from oracle import parallel
-    design = np.array([[1, 0], [1, 0], [0, 1], [0, 1]], dtype=bool)
-    if ins is None:
-        ins = cpu_inputs(sample)
-    t0 = time.perf_counter()
-    res = parallel.run_to_qvalues(ins, design, dist_max=sample['dist_max'],
-                                  n_threads=n_threads)
-    dt = time.perf_counter() - t0
-    n_px = sum(len(st['row']) for st in res['chroms'])
-    return n_px, dt
-
-
-def sample_desc(sample=CPU_SAMPLE):
-    sizes = list(sample['chroms'].values())
-    return ('%d chromosomes of %d-%d bins of the same generator, 2-vs-2, '
-            'dist cap %d bins, full run_to_qvalues arithmetic in memory'
-            % (len(sizes), min(sizes), max(sizes), sample['dist_max']))
+def time_reference(n_bins, steps=1, n_threads=-1):
+    """``steps`` timed runs of the reference's run_to_qvalues over a bounded
+    sample of ~n_bins bins.  Returns (pixels per run, list of seconds,
+    sample description, kind)."""
+    from oracle import reference_bench as rb
+    chroms = rb.sample_chroms(n_bins)
+    ds = rb.Dataset(chroms)
+    try:
+        n_px, times = 0, []
+        for _ in range(steps):
+            n_px, dt = rb.run_once(ds, n_threads)
+            times.append(dt)
+    finally:
+        ds.close()
+    return n_px, times, rb.describe(chroms), rb.kind()
 
 
 def run_reference(args, cfg):
+    """Reference arm: the reference's own CPU implementation, all host cores
+    (its process pools, n_threads=-1), files in -> files out.  Each step is
+    the same bounded sample of the workload, sized from a calibration run so
+    that the K steps end within REF_BUDGET_S; when the budget allows, the
+    sample is the whole of BASELINE configs[0] (chr18 + chr19)."""
     if int(os.environ.get('RANK', '0')) != 0:
         return
+    from oracle import reference_bench as rb
     cores = os.cpu_count() or 1
-    rates, times = [], []
-    ins = cpu_inputs(REF_SAMPLE)
-    for _ in range(min(args.warmup, 1)):     # page in numpy / scipy once
-        time_oracle(-1, CPU_SAMPLE)
-    for _ in range(args.steps):
-        n_px, dt = time_oracle(-1, REF_SAMPLE, ins)
-        rates.append(n_px / dt)
-        times.append(dt)
-    value = float(np.mean(rates))
+    # warm-up = calibration: small runs that page in numpy / scipy / pandas
+    # and measure the rate the sample is sized from
+    rate = None
+    for _ in range(max(1, min(args.warmup, 2))):
+        n_px, times, _, _ = time_reference(700, 1)
+        rate = n_px / times[-1]
+    per_step_px = rate * REF_BUDGET_S / max(args.steps, 1)
+    n_bins = int(per_step_px / (rb.DIST_MAX + 1))
+    if os.environ.get('H3D_REF_BINS'):
+        n_bins = int(os.environ['H3D_REF_BINS'])
+    n_px, times, desc, kind = time_reference(n_bins, args.steps)
+    value = n_px / float(np.mean(times))
     line = dict(
         impl='reference', metric='pixels/sec through run_to_qvalues',
         value=value, unit='pixels/s', n_gpus=args.gpus, steps=args.steps,
         warmup=args.warmup, ms_per_step=1e3 * float(np.mean(times)),
         higher_is_better=True, scaling='strong', vs_baseline=None,
         dtype='f64', data='synthetic',
-        config=dict(workload=cfg['desc'], timing='host wall clock'),
+        # the workload the GPU arm runs; every step here is a bounded sample
+        # of it (chromosomes of the same generator), named in ``sample``
+        config=dict(workload=cfg['desc'], sample=desc,
+                    sample_union_pixels=int(n_px),
+                    timing='host wall clock around run_to_qvalues()',
+                    reference='unmodified hic3defdr v0.2.1 (lib5c shim, '
+                              'stable equal_bin), n_threads=-1'
+                    if kind == 'reference' else 'oracle port (reference tree '
+                    'not found)'),
         cpu_baseline=dict(value=value, unit='pixels/s', cores=cores,
-                          kind='port', sample=sample_desc(REF_SAMPLE)),
+                          kind=kind, sample=desc),
         e2e=dict(value=value, unit='pixels/s', h2d_bytes_per_step=0,
                  d2h_bytes_per_step=0),
         gpu_launches=0)
@@ -303,6 +308,120 @@ def stage_rooflines(stage_ms, n_px, n_d, n_reps, fp64_peak_tflops):
                              frac=round(work / ms / 1e9 / fp64_peak_tflops, 4))
         out[name] = entry
     return out
+
+
+# --------------------------------------------------------------------------
+# N > 1: the sharded run against the one-process run of the same inputs
+# (outside every timed region)
+# --------------------------------------------------------------------------
+PARITY_KEYS = ('row', 'col', 'raw', 'size_factors', 'scaled', 'disp_idx',
+               'disp', 'pvalues', 'llr', 'mu_hat_null', 'mu_hat_alt',
+               'qvalues')
+
+
+def _bits_sum(t):
+    """wrapping 64-bit sum of the raw bit patterns of a tensor: equal arrays
+    give equal sums whatever way they are cut into slices"""
+    import torch
+    t = t.contiguous()
+    if t.numel() == 0:
+        return 0
+    if t.element_size() == 8:
+        v = t.view(torch.int64)
+    elif t.element_size() == 4:
+        v = t.view(torch.int32).to(torch.int64)
+    else:
+        v = t.view(torch.uint8).to(torch.int64)
+    # position-weighted as well, so that a permutation does not cancel out
+    return int(v.sum().item()) & 0xFFFFFFFFFFFFFFFF
+
+
+def _state_record(st, with_sha):
+    import hashlib
+    import torch
+    rec = {k: [_bits_sum(st[k]), int(st[k].shape[0])] for k in PARITY_KEYS}
+    rec['n_sig'] = int((st['qvalues'] < 0.05).sum().item())
+    if with_sha:
+        rec['q_sha'] = hashlib.sha256(
+            st['qvalues'].cpu().numpy().tobytes()).hexdigest()
+        rec['p_sha'] = hashlib.sha256(
+            st['pvalues'].cpu().numpy().tobytes()).hexdigest()
+    return rec
+
+
+def parity_vs_one_process(cfg, names, mine, row_sharded, step_device, design,
+                          kw, rank):
+    """Runs one more sharded step, then rank 0 recomputes the whole workload
+    as a one-process run (hdist.single_process: no collectives) and compares:
+    disp_per_dist, and per chromosome the bit patterns of all twelve output
+    arrays (wrapping 64-bit sums, composable over row slices), the number of
+    pixels with q < 0.05 and -- when ranks hold whole chromosomes -- the
+    sha256 of the p- and q-value arrays."""
+    import hashlib
+    import torch
+    import torch.distributed as td
+    from hic3defdr_b200 import dist as hdist
+    from hic3defdr_b200 import engine, staging
+    states, dpd, _, _ = step_device()
+    torch.cuda.synchronize()
+    local = {c: _state_record(st, not row_sharded)
+             for c, st in zip(mine, states)}
+    del states
+    gathered = [None] * td.get_world_size()
+    td.all_gather_object(gathered, (local, dpd))
+    if rank != 0:
+        td.barrier()
+        return None
+    torch.cuda.empty_cache()
+    inputs = []
+    for c in names:
+        n = cfg['chroms'][c]
+        mats, bias = gen_chrom_device(n, cfg['n_reps'], cfg['dist_max'],
+                                      20261018 + 1000 + 100 * names.index(c),
+                                      cfg['amp'],
+                                      res_scale=cfg.get('res_scale', 1.0))
+        inputs.append((staging.csr_to_device(mats, n), bias))
+    kw1 = dict(kw, row_sharded=False)
+    with hdist.single_process():
+        states1, dpd1, _, _ = engine.run_to_qvalues(inputs, design, **kw1)
+    torch.cuda.synchronize()
+    want = {c: _state_record(st, not row_sharded)
+            for c, st in zip(names, states1)}
+    del states1, inputs
+    ok = np.isfinite(dpd1)
+    same_nan = bool(np.array_equal(ok, np.isfinite(dpd)))
+    rel = float(np.max(np.abs(dpd[ok] - dpd1[ok]) / np.abs(dpd1[ok]))) \
+        if same_nan and ok.any() else None
+    tables_equal = all(np.array_equal(g[1], dpd1, equal_nan=True)
+                       for g in gathered)
+    mismatched = []
+    n_sig_n, sha_n = 0, {}
+    for c in names:
+        recs = [g[0][c] for g in gathered if c in g[0]]
+        for k in PARITY_KEYS:
+            bits = sum(r[k][0] for r in recs) & 0xFFFFFFFFFFFFFFFF
+            rows = sum(r[k][1] for r in recs)
+            if [bits, rows] != want[c][k]:
+                mismatched.append('%s_%s' % (k, c))
+        n_sig_n += sum(r['n_sig'] for r in recs)
+        if not row_sharded:
+            sha_n[c] = (recs[0]['q_sha'], recs[0]['p_sha'])
+    rec = dict(
+        what='one more N-rank step vs the same inputs recomputed by rank 0 '
+             'as a one-process run; outside the timed region',
+        disp_per_dist_max_rel=rel, disp_per_dist_equal_on_all_ranks=tables_equal,
+        n_sig_q_lt_0_05=[n_sig_n, sum(w['n_sig'] for w in want.values())],
+        arrays_compared=len(PARITY_KEYS) * len(names),
+        arrays_with_different_bits=mismatched[:20],
+        all_outputs_bit_identical=(not mismatched) and tables_equal)
+    if not row_sharded:
+        cat = lambda d, i: hashlib.sha256(
+            ''.join(d[c][i] for c in names).encode()).hexdigest()
+        w = {c: (want[c]['q_sha'], want[c]['p_sha']) for c in names}
+        rec['q_sha256'] = [cat(sha_n, 0), cat(w, 0)]
+        rec['p_sha256'] = [cat(sha_n, 1), cat(w, 1)]
+    td.barrier()
+    return rec
 
 
 # --------------------------------------------------------------------------
@@ -485,6 +604,10 @@ def main():
             trace.report('step_e2e, rank 0, per step', args.steps)
     sampler.stop_flag = True
     sampler.join()
+    parity = None
+    if world > 1 and not os.environ.get('H3D_NO_PARITY'):
+        parity = parity_vs_one_process(cfg, names, mine, row_sharded,
+                                       step_device, design, kw, rank)
     h2d = sum(h.nbytes for h, _ in host_inputs)
     in_bytes = sum(sum(t.numel() * t.element_size()
                        for ts in (c.indptr, c.indices, c.data) for t in ts) +
@@ -515,9 +638,10 @@ def main():
             pass
         cpu = None
         if not args.no_cpu_baseline and world == 1:     # reported at N = 1 only
-            n_cpu, dt_cpu = time_oracle(0)
-            cpu = dict(value=n_cpu / dt_cpu, unit='pixels/s', cores=1,
-                       kind='port', sample=sample_desc())
+            n_cpu, t_cpu, desc_cpu, kind_cpu = time_reference(CPU_BASELINE_BINS)
+            cpu = dict(value=n_cpu / t_cpu[0], unit='pixels/s',
+                       cores=os.cpu_count() or 1, kind=kind_cpu,
+                       sample=desc_cpu)
         step_ms = ms / args.steps
         line = dict(
             metric='pixels/sec through run_to_qvalues',
@@ -559,6 +683,7 @@ def main():
             stages=stage_rooflines(stage_ms, n_px_local, n_d_local,
                                    cfg['n_reps'], peak),
             cpu_baseline=cpu,
+            parity_vs_n1=parity,
             host_ms_per_step=step_wall,
             clocks=sampler.summary())
         print(json.dumps(line))

@@ -49,6 +49,9 @@ SIGNATURES = {
     'h3d_estimate_dispersion': (c_int, [vp, vp, c_ll, vp, c_int, vp, c_int,
                                         c_int, c_int, vp, vp, vp, c_sz, vp]),
     'h3d_estimate_dispersion_ws_bytes': (c_sz, [c_ll, c_int, c_int, c_int]),
+    'h3d_equalize': (c_int, [vp, vp, c_ll, c_ll, c_int, c_dbl, vp, vp, vp,
+                             c_sz, vp]),
+    'h3d_equalize_ws_bytes': (c_sz, [c_ll]),
     'h3d_lowess': (c_int, [vp, vp, c_int, c_dbl, c_int, c_dbl, vp, vp, c_sz,
                            vp]),
     'h3d_lowess_ws_bytes': (c_sz, [c_int]),

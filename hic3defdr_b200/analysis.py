@@ -117,7 +117,8 @@ class HiC3DeFDR(object):
 
     def __init__(self, raw_npz_patterns, bias_patterns, chroms, design, outdir,
                  dist_thresh_min=4, dist_thresh_max=200, bias_thresh=0.1,
-                 mean_thresh=1.0, loop_patterns=None, res=None):
+                 mean_thresh=1.0, loop_patterns=None, res=None,
+                 _write_pickle=True):
         self.raw_npz_patterns = raw_npz_patterns
         self.bias_patterns = bias_patterns
         self.chroms = chroms
@@ -134,11 +135,16 @@ class HiC3DeFDR(object):
         self.res = res
         state = self.__dict__.copy()
         del state['outdir']
-        if hdist.rank() == 0:
-            check_outdir(self.picklefile)
-            with open(self.picklefile, 'wb') as handle:
-                pickle.dump(state, handle, -1)
-        hdist.barrier()
+        if _write_pickle:
+            if hdist.rank() == 0:
+                check_outdir(self.picklefile)
+                # written under a temporary name and renamed: a concurrent
+                # reader never sees a truncated file
+                tmp = '%s.tmp%d' % (self.picklefile, os.getpid())
+                with open(tmp, 'wb') as handle:
+                    pickle.dump(state, handle, -1)
+                os.replace(tmp, self.picklefile)
+            hdist.barrier()
         self._cache = {}
         self._shards = {}
         self._writer = None
@@ -152,8 +158,13 @@ class HiC3DeFDR(object):
 
     @classmethod
     def load(cls, outdir):
+        # the reference re-dumps the pickle it has just read
+        # (constructor.py:82-86 runs inside load); with several ranks that
+        # rewrite could truncate the file under a slower reader, so load()
+        # only reads
         with open('%s/pickle' % outdir, 'rb') as handle:
-            return cls(outdir=outdir, **pickle.load(handle))
+            state = pickle.load(handle)
+        return cls(outdir=outdir, _write_pickle=False, **state)
 
     def _design(self):
         return np.asarray(self.design.values).astype(bool)
@@ -500,10 +511,12 @@ class HiC3DeFDR(object):
                       weighted_lowess=True, n_threads=-1):
         """analysis/analysis.py:135-223."""
         eprint('estimating dispersion')
-        if not isinstance(estimator, str) or estimator not in ops.ESTIMATORS:
+        if not callable(estimator) and estimator not in ops.ESTIMATORS:
             raise ValueError(
-                "estimator must be one of 'qcml', 'cml', 'mme' on the GPU "
-                "path (python callables cannot run on the device)")
+                "estimator must be 'qcml', 'cml', 'mme' (device kernels) or a "
+                "function (data, f=...) -> dispersion, which is called on the "
+                "host with the pooled pixels of every (distance, condition) "
+                "bin, analysis/analysis.py:164-165")
         eprint('  loading data')
         mine = self._my_chroms()
         states = [self._chrom_state(
@@ -688,12 +701,18 @@ class HiC3DeFDR(object):
                 pattern = '%s/<class>_%g_%i_<chrom>.tsv' % (self.outdir, f, s)
                 path = lambda cls, chrom: pattern.replace('<class>', cls) \
                     .replace('<chrom>', chrom)
-                if not all(os.path.isfile(path('insig', c))
-                           for c in self.chroms):
+                # threshold() / classify() contain barriers: every rank must
+                # take the same branch, so rank 0 looks at the files and the
+                # others follow its decision
+                need = hdist.broadcast_flags([
+                    not all(os.path.isfile(path('insig', c))
+                            for c in self.chroms),
+                    not all(os.path.isfile(path(cond, c))
+                            for cond in self.design.columns
+                            for c in self.chroms)])
+                if need[0]:
                     self.threshold(fdr=f, cluster_size=s)
-                if not all(os.path.isfile(path(cond, c))
-                           for cond in self.design.columns
-                           for c in self.chroms):
+                if need[1]:
                     self.classify(fdr=f, cluster_size=s)
                 if hdist.rank() != 0:
                     continue

@@ -12,13 +12,17 @@
 // Brent bracket) lives in device arrays updated by a one-thread-per-bin kernel.
 //   equalize_kernel : per pixel fit_mu + q2q pseudo-data at the bin's current
 //                     dispersion (FP64 special functions; the dominant cost)
-//   nll_kernel      : per-chunk partial sums of the conditional NB
-//                     log-likelihood at the bin's current Brent abscissa
-//   step_kernel     : sums a bin's partials in a fixed order (deterministic),
-//                     advances scipy's bounded Brent state machine, applies
+//   nll_kernel      : the conditional NB log-likelihood of every searching bin
+//                     at its current Brent abscissa, summed in 128-bit fixed
+//                     point (exact, hence independent of the pixel order and
+//                     of how many GPUs pooled the pixels)
+//   step_kernel     : advances scipy's bounded Brent state machine, applies
 //                     the qCML stopping rule |delta disp| <= 1e-4
+// The host queues rounds of these ahead of the device and reads the per-round
+// convergence counters from mapped memory without synchronising the stream.
 // FP64-pipe bound: ~44 k FP64 instruction-
 // equivalents per pixel against 16 R_c bytes read + 8 R_c written per sweep.
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -61,6 +65,9 @@ __global__ void init_problems_kernel(Problem* __restrict__ prob, const long long
     q.outer_iters = 0; q.nfev_total = 0;
     q.disp = (q.n_px > 0) ? 0.01 : NAN;                 // dispersion.py:33 / analysis.py:205
     q.status = (q.n_px > 0) ? ST_NEED_EQ : ST_EMPTY;
+    // a bin that waits for pseudo-data has its Brent search already set up: the
+    // likelihood kernel of the same round evaluates the first abscissa
+    brent_begin(q.brent, kDeltaLo, kDeltaHi);
     (void)estimator;
 }
 
@@ -312,18 +319,61 @@ equalize_kernel(const double* __restrict__ x, const double* __restrict__ f, long
     }
 }
 
-// deterministic block sum: shuffle tree inside warps, then warp 0 adds the 8
-// warp results in index order
-__device__ __forceinline__ double block_sum_256(double v, double* sh) {
-    v = warp_sum(v);
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+// Order-independent sums.  Every per-pixel term is converted to a 128-bit
+// fixed-point number (64 integer bits, 64 fractional bits; the conversion is a
+// pure function of the value) and the terms are added as integers, which is
+// associative and commutative: the sum of a bin does not depend on how its
+// pixels are ordered, chunked, or spread over thread blocks -- and therefore not
+// on how many GPUs pooled them.  Non-finite terms (and
+// anything beyond +-2^62) are counted in ``bad`` instead.
+struct Fix128 {
+    unsigned long long lo;   // fractional part, units of 2^-64
+    long long hi;            // integer part (floor)
+    long long bad;           // number of non-representable terms
+    long long cnt;           // number of terms (used by the MME mean)
+};
+
+// per-thread accumulator (registers): count-free, 32-bit flag
+struct FixAcc { unsigned long long lo; long long hi; int bad; };
+
+__device__ __forceinline__ void fix_add(FixAcc& a, double v) {
+    if (!(fabs(v) < 4.611686018427387904e18)) { a.bad += 1; return; }
+    const double fl = floor(v);
+    const unsigned long long l = __double2ull_rz((v - fl) * 18446744073709551616.0);
+    a.lo += l;
+    a.hi += __double2ll_rz(fl) + (long long)(a.lo < l);
+}
+
+__host__ __device__ __forceinline__ double fix_value(const Fix128& a) {
+    return (double)a.hi + (double)a.lo * 5.421010862427522170e-20;     // 2^-64
+}
+
+// block-wide sum of the threads' accumulators (and of a per-thread term
+// count); the result is valid in thread 0
+__device__ __forceinline__ Fix128 block_sum_fix(FixAcc v, int cnt, Fix128* sh) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long lo = __shfl_down_sync(0xffffffffu, v.lo, o);
+        const long long hi = __shfl_down_sync(0xffffffffu, v.hi, o);
+        v.bad += __shfl_down_sync(0xffffffffu, v.bad, o);
+        cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+        v.lo += lo;
+        v.hi += hi + (long long)(v.lo < lo);
+    }
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = Fix128{v.lo, v.hi, (long long)v.bad, (long long)cnt};
     __syncthreads();
-    double t = 0.0;
-    if (threadIdx.x == 0) for (int w = 0; w < 8; ++w) t += sh[w];
+    Fix128 t = {0ull, 0ll, 0ll, 0ll};
+    if (threadIdx.x == 0)
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+            t.lo += sh[w].lo;
+            t.hi += sh[w].hi + (long long)(t.lo < sh[w].lo);
+            t.bad += sh[w].bad;
+            t.cnt += sh[w].cnt;
+        }
     return t;
 }
 
-// conditional NB negative log-likelihood partials (dispersion.py:72-75):
+// conditional NB negative log-likelihood (dispersion.py:72-75):
 //   sum_px [ sum_k lgamma(y_k + r) + lgamma(n r) - lgamma(z + n r) - n lgamma(r) ]
 // Every log-gamma goes through Stirling's series at an argument >= 10
 // (shifted up by the recurrence when smaller); the "- x" terms of the
@@ -332,21 +382,38 @@ __device__ __forceinline__ double block_sum_256(double v, double* sh) {
 //   sum_k [core(x_k) - n_k] - [core(X) - N] + (R_c - 1) .5 ln 2pi,
 // core(x) = (x - .5) ln x + corr(x) at the shifted argument minus the log of
 // the shift product, n = number of unit shifts.
+// The per-pixel terms are added in 128-bit fixed point (order independent, see
+// Fix128) into the bin's accumulator.
 // 8 resident CTAs per SM (32 registers, 44 bytes of spills) against 6 without
 // spills: 35.4 -> 34.5 ms per step -- the kernel waits on dependent FP64 latency
 #ifndef H3D_NLL_MIN_BLOCKS
 #define H3D_NLL_MIN_BLOCKS 8
 #endif
+
+// adds a block's total to the (segment, condition) accumulator; integer
+// atomics commute, so the result is exact whatever the arrival order
+__device__ __forceinline__ void fix_atomic_add(Fix128* dst, const Fix128& t) {
+    if (t.lo) {
+        const unsigned long long old = atomicAdd(&dst->lo, t.lo);
+        const long long carry = (long long)(old + t.lo < old);
+        if (t.hi + carry) atomicAdd((unsigned long long*)&dst->hi, (unsigned long long)(t.hi + carry));
+    } else if (t.hi) {
+        atomicAdd((unsigned long long*)&dst->hi, (unsigned long long)t.hi);
+    }
+    if (t.bad) atomicAdd((unsigned long long*)&dst->bad, (unsigned long long)t.bad);
+    if (t.cnt) atomicAdd((unsigned long long*)&dst->cnt, (unsigned long long)t.cnt);
+}
+
 template <int MAXRC>
 __global__ void __launch_bounds__(256, H3D_NLL_MIN_BLOCKS)
 nll_kernel(const double* __restrict__ pseudo, long long ld, const int* __restrict__ chunk_seg,
            const long long* __restrict__ chunk_lo, const long long* __restrict__ seg_start,
-           CondReps cr, const Problem* __restrict__ prob, double* __restrict__ partial, int n_chunks) {
-    __shared__ double sh[8];
+           CondReps cr, const Problem* __restrict__ prob, Fix128* __restrict__ acc) {
+    __shared__ Fix128 sh[8];
     const int c = blockIdx.y;
     const int s = chunk_seg[blockIdx.x];
     const Problem& q = prob[s * cr.n_conds + c];
-    if (q.status != ST_IN_BRENT) return;
+    if (q.status != ST_IN_BRENT && q.status != ST_NEED_EQ) return;
     const double delta = q.brent.x_eval;
     const double r = 1.0 / delta - 1.0;
     const int nr = cr.n_in[c];
@@ -357,7 +424,7 @@ nll_kernel(const double* __restrict__ pseudo, long long ld, const int* __restric
     const long long seg_hi = seg_start[s + 1];
     const long long hi = (lo + kChunk < seg_hi) ? lo + kChunk : seg_hi;
     const double* __restrict__ base = pseudo + (long long)cr.pseudo_row[c] * ld;
-    double acc = 0.0;
+    FixAcc a = {0ull, 0ll, 0};
     if (r >= 10.0) {
         for (long long i = lo + threadIdx.x; i < hi; i += 256) {
             double z = 0.0, t = 0.0;
@@ -369,7 +436,7 @@ nll_kernel(const double* __restrict__ pseudo, long long ld, const int* __restric
                     t += stirling_core(y + r);
                 }
             }
-            acc += (t + cst) - stirling_core(z + nrr);
+            fix_add(a, (t + cst) - stirling_core(z + nrr));
         }
     } else {
         // uniform shift of every argument by n_shift units (see stirling_core_shifted);
@@ -386,29 +453,29 @@ nll_kernel(const double* __restrict__ pseudo, long long ld, const int* __restric
                     t += stirling_core_shifted(y + r, n_shift);
                 }
             }
-            acc += (t + cst_s) - stirling_core_shifted(z + nrr, n_shift);
+            fix_add(a, (t + cst_s) - stirling_core_shifted(z + nrr, n_shift));
         }
     }
-    const double tot = block_sum_256(acc, sh);
-    if (threadIdx.x == 0) partial[(long long)c * n_chunks + blockIdx.x] = tot;
+    const Fix128 tot = block_sum_fix(a, 0, sh);
+    if (threadIdx.x == 0) fix_atomic_add(&acc[s * cr.n_conds + c], tot);
 }
 
-// MME partials: sum and count of the finite per-pixel estimates
+// MME: sum and count of the non-NaN per-pixel estimates
 // (dispersion.py:101-105, 129-131)
 template <int MAXRC>
 __global__ void __launch_bounds__(256)
 mme_kernel(const double* __restrict__ x, const double* __restrict__ f, long long ld,
            const int* __restrict__ chunk_seg, const long long* __restrict__ chunk_lo,
-           const long long* __restrict__ seg_start, CondReps cr, double* __restrict__ partial,
-           double* __restrict__ partial_cnt, int n_chunks) {
-    __shared__ double sh[8];
+           const long long* __restrict__ seg_start, CondReps cr, Fix128* __restrict__ acc) {
+    __shared__ Fix128 sh[8];
     const int c = blockIdx.y;
     const int s = chunk_seg[blockIdx.x];
     const long long lo = chunk_lo[blockIdx.x];
     const long long seg_hi = seg_start[s + 1];
     const long long hi = (lo + kChunk < seg_hi) ? lo + kChunk : seg_hi;
     const int nr = cr.n_in[c];
-    double acc = 0.0, cntv = 0.0;
+    FixAcc a = {0ull, 0ll, 0};
+    int n_est = 0;
     for (long long i = lo + threadIdx.x; i < hi; i += 256) {
         double v[MAXRC];
         double m = 0.0;
@@ -428,53 +495,34 @@ mme_kernel(const double* __restrict__ x, const double* __restrict__ f, long long
             if (k < nr) { const double dlt = v[k] - m; ss += dlt * dlt; }
         const double var = ss / (double)(nr - 1);
         const double est = (var - m) / (m * m);             // inverse_mvr (scaled_nb.py:68)
-        if (!isnan(est)) { acc += est; cntv += 1.0; }
+        if (!isnan(est)) { fix_add(a, est); n_est += 1; }   // nanmean: infinities stay in
     }
-    const double tot = block_sum_256(acc, sh);
-    __syncthreads();
-    const double tc = block_sum_256(cntv, sh);
-    if (threadIdx.x == 0) {
-        partial[(long long)c * n_chunks + blockIdx.x] = tot;
-        partial_cnt[(long long)c * n_chunks + blockIdx.x] = tc;
-    }
+    const Fix128 tot = block_sum_fix(a, n_est, sh);
+    if (threadIdx.x == 0) fix_atomic_add(&acc[s * cr.n_conds + c], tot);
 }
 
-// one thread per problem.  mode 0: start a Brent search for bins whose
-// pseudo-data were just (re)computed; mode 1: consume the NLL partials;
-// mode 2: finish MME.
-__global__ void step_kernel(Problem* __restrict__ prob, const int* __restrict__ seg_chunk_start,
-                            const double* __restrict__ partial, const double* __restrict__ partial_cnt,
-                            int n_chunks, int n_seg, int n_conds, int estimator, int mode,
-                            Counters* cnt) {
+// one thread per problem.  mode 1: consume the bin's NLL accumulator, advance
+// the Brent search and the qCML fixed point; mode 2: finish MME.
+__global__ void step_kernel(Problem* __restrict__ prob, Fix128* __restrict__ acc,
+                            int n_prob, int estimator, int mode, Counters* cnt) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_seg * n_conds) return;
-    const int s = p / n_conds, c = p % n_conds;
+    if (p >= n_prob) return;
     Problem& q = prob[p];
     if (mode == 2) {
         if (q.status == ST_EMPTY) return;
-        double sum = 0.0, n = 0.0;
-        for (int k = seg_chunk_start[s]; k < seg_chunk_start[s + 1]; ++k) {
-            sum += partial[(long long)c * n_chunks + k];
-            n += partial_cnt[(long long)c * n_chunks + k];
-        }
-        q.disp = sum / n;                                   // nanmean
+        const Fix128 a = acc[p];
+        // nanmean (dispersion.py:131); an infinite per-pixel estimate makes it
+        // infinite (or NaN) there, NaN here
+        q.disp = a.bad ? NAN : fix_value(a) / (double)a.cnt;
         q.status = ST_DONE;
         return;
     }
-    if (mode == 0) {
-        if (q.status != ST_NEED_EQ) return;
-        brent_begin(q.brent, kDeltaLo, kDeltaHi);
-        q.status = ST_IN_BRENT;
-        atomicAdd(&cnt->n_in_brent, 1);
-        return;
-    }
-    if (q.status != ST_IN_BRENT) return;
-    double sum = 0.0;
-    for (int k = seg_chunk_start[s]; k < seg_chunk_start[s + 1]; ++k)
-        sum += partial[(long long)c * n_chunks + k];
-    const double fu = -sum;
+    if (q.status != ST_IN_BRENT && q.status != ST_NEED_EQ) return;
+    const Fix128 a = acc[p];
+    acc[p] = Fix128{0ull, 0ll, 0ll, 0ll};
+    const double fu = a.bad ? NAN : -fix_value(a);
     const bool more = brent_advance(q.brent, fu, kBrentXatol, kBrentMaxfun);
-    if (more) { atomicAdd(&cnt->n_in_brent, 1); return; }
+    if (more) { q.status = ST_IN_BRENT; atomicAdd(&cnt->n_in_brent, 1); return; }
     q.nfev_total += q.brent.num;
     if (q.brent.flag != 0) {                                // assert res.success (dispersion.py:78)
         q.status = ST_FAILED; q.disp = NAN;
@@ -488,17 +536,31 @@ __global__ void step_kernel(Problem* __restrict__ prob, const int* __restrict__ 
     const double dl = fabs(q.disp - nd);                    // dispersion.py:36-42
     q.disp = nd;
     if (dl > kQcmlTol && q.outer_iters < H3D_QCML_MAX_OUTER) {
+        // next outer iteration: pseudo-data at the new dispersion, new search
+        brent_begin(q.brent, kDeltaLo, kDeltaHi);
         q.status = ST_NEED_EQ; atomicAdd(&cnt->n_need_eq, 1);
     } else {
         q.status = (dl > kQcmlTol) ? ST_DONE_CAPPED : ST_DONE;     // see include/h3d.h
     }
 }
 
-__global__ void reset_counters_kernel(Counters* cnt) { cnt->n_need_eq = 0; cnt->n_in_brent = 0; }
+// End of a round: the convergence counters go to the host through pinned,
+// device-mapped memory (written by an SM: must not queue on the copy engine
+// behind bulk output copies of other streams), sequence number last; the
+// per-round counters are cleared for the next round.
+struct RoundSlot { unsigned long long seq; int n_need_eq, n_in_brent, n_failed, n_fit_failed; unsigned long long pad; };
+static_assert(sizeof(RoundSlot) == 32, "RoundSlot layout");
 
-// device -> pinned, device-mapped host memory by the SMs: the per-round
-// convergence counters (and the final table) must not queue on the copy engine
-// behind bulk output copies of other streams
+__global__ void publish_round_kernel(Counters* cnt, volatile RoundSlot* slot, unsigned long long seq) {
+    slot->n_need_eq = cnt->n_need_eq;
+    slot->n_in_brent = cnt->n_in_brent;
+    slot->n_failed = cnt->n_failed;
+    slot->n_fit_failed = cnt->n_fit_failed;
+    __threadfence_system();
+    slot->seq = seq;
+    cnt->n_need_eq = 0; cnt->n_in_brent = 0;
+}
+
 __global__ void publish_words_kernel(const unsigned long long* __restrict__ src,
                                      volatile unsigned long long* __restrict__ dst, int n_words) {
     for (int i = threadIdx.x; i < n_words; i += blockDim.x) dst[i] = src[i];
@@ -522,25 +584,51 @@ __global__ void collect_kernel(const Problem* __restrict__ prob, int n, double* 
     if (threadIdx.x == 0) { stats[0] = it_sum; stats[1] = fev_sum; stats[2] = eq_sum; stats[3] = cap_sum; }
 }
 
+// one problem per condition over a single segment, waiting for pseudo-data at a
+// given dispersion (h3d_equalize)
+__global__ void single_bin_problems_kernel(Problem* prob, int n_conds, long long n_px, double alpha,
+                                           Counters* cnt) {
+    const int p = threadIdx.x;
+    if (p == 0) { cnt->n_need_eq = 0; cnt->n_in_brent = 0; cnt->n_failed = 0; cnt->n_fit_failed = 0; }
+    if (p >= n_conds) return;
+    prob[p].n_px = n_px; prob[p].outer_iters = 0; prob[p].nfev_total = 0;
+    prob[p].disp = alpha; prob[p].status = ST_NEED_EQ;
+}
+
 }  // namespace h3d
 
 using namespace h3d;
 
-// process-wide pinned scratch for control read-backs (grown on demand; the
-// library is driven by one host thread per process, one process per GPU)
-static void* g_pinned = nullptr;
-static size_t g_pinned_bytes = 0;
+// per-thread pinned scratch for control read-backs (grown on demand): entry
+// points may be driven from several host threads, each with its own stream
+struct PinnedScratch {
+    void* p = nullptr;
+    size_t bytes = 0;
+    ~PinnedScratch() { if (p) cudaFreeHost(p); }
+};
+static thread_local PinnedScratch g_pinned;
 static int pinned_scratch(size_t bytes, void** host, void** dev) {
-    if (bytes > g_pinned_bytes) {
-        if (g_pinned) cudaFreeHost(g_pinned);
-        g_pinned = nullptr; g_pinned_bytes = 0;
-        H3D_CHECK(cudaHostAlloc(&g_pinned, bytes, cudaHostAllocPortable | cudaHostAllocMapped));
-        g_pinned_bytes = bytes;
+    if (bytes > g_pinned.bytes) {
+        if (g_pinned.p) cudaFreeHost(g_pinned.p);
+        g_pinned.p = nullptr; g_pinned.bytes = 0;
+        H3D_CHECK(cudaHostAlloc(&g_pinned.p, bytes, cudaHostAllocPortable | cudaHostAllocMapped));
+        g_pinned.bytes = bytes;
     }
-    *host = g_pinned;
-    H3D_CHECK(cudaHostGetDevicePointer(dev, g_pinned, 0));
+    *host = g_pinned.p;
+    H3D_CHECK(cudaHostGetDevicePointer(dev, g_pinned.p, 0));
     return H3D_OK;
 }
+
+// CUDA events that are destroyed on every return path
+struct EventPool {
+    std::vector<cudaEvent_t> ev;
+    int create(int n) {
+        ev.assign(n, nullptr);
+        for (int k = 0; k < n; ++k) H3D_CHECK(cudaEventCreate(&ev[k]));
+        return H3D_OK;
+    }
+    ~EventPool() { for (cudaEvent_t e : ev) if (e) cudaEventDestroy(e); }
+};
 
 static long long count_chunks(const long long* seg_start_host, int n_seg) {
     long long n = 0;
@@ -548,16 +636,85 @@ static long long count_chunks(const long long* seg_start_host, int n_seg) {
     return n;
 }
 
+static int make_cond_reps(const unsigned char* design_host, int n_reps, int n_conds, CondReps* cr,
+                          int* rows_out, int* max_rc_out) {
+    cr->n_conds = n_conds;
+    int rows = 0, max_rc = 0;
+    for (int c = 0; c < H3D_MAX_CONDS; ++c) {
+        cr->n_in[c] = 0; cr->pseudo_row[c] = rows;
+        for (int k = 0; k < H3D_MAX_REPS; ++k) cr->rep[c][k] = 0;
+        if (c >= n_conds) continue;
+        for (int r = 0; r < n_reps; ++r)
+            if (design_host[r * n_conds + c]) cr->rep[c][cr->n_in[c]++] = r;
+        H3D_REQUIRE(cr->n_in[c] >= 1, "condition without replicates");
+        rows += cr->n_in[c];
+        if (cr->n_in[c] > max_rc) max_rc = cr->n_in[c];
+    }
+    *rows_out = rows; *max_rc_out = max_rc;
+    return H3D_OK;
+}
+
+// chunk tables of the segments, built on the host and copied
+struct ChunkTables { int n_chunks; int* chunk_seg; long long* chunk_lo; long long* seg_start; };
+static int make_chunk_tables(const long long* seg_start_host, int n_seg, Workspace& w, cudaStream_t st,
+                             ChunkTables* t) {
+    const long long n_chunks_ll = count_chunks(seg_start_host, n_seg);
+    H3D_REQUIRE(n_chunks_ll < 2147483647LL, "too many chunks");
+    const int n_chunks = (int)n_chunks_ll;
+    std::vector<int> h_chunk_seg(n_chunks);
+    std::vector<long long> h_chunk_lo(n_chunks);
+    int k = 0;
+    for (int s = 0; s < n_seg; ++s)
+        for (long long lo = seg_start_host[s]; lo < seg_start_host[s + 1]; lo += kChunk) {
+            h_chunk_seg[k] = s; h_chunk_lo[k] = lo; ++k;
+        }
+    t->n_chunks = n_chunks;
+    t->chunk_seg = w.take<int>(n_chunks);
+    t->chunk_lo = w.take<long long>(n_chunks);
+    t->seg_start = w.take<long long>(n_seg + 1);
+    if (!t->chunk_seg || !t->chunk_lo || !t->seg_start) {
+        set_error("dispersion workspace too small (%zu bytes given)", w.size);
+        return H3D_ERR_WORKSPACE;
+    }
+    H3D_CHECK(cudaMemcpyAsync(t->chunk_seg, h_chunk_seg.data(), (size_t)n_chunks * 4, cudaMemcpyHostToDevice, st));
+    H3D_CHECK(cudaMemcpyAsync(t->chunk_lo, h_chunk_lo.data(), (size_t)n_chunks * 8, cudaMemcpyHostToDevice, st));
+    H3D_CHECK(cudaMemcpyAsync(t->seg_start, seg_start_host, (size_t)(n_seg + 1) * 8, cudaMemcpyHostToDevice, st));
+    // the host vectors must outlive the async copies
+    H3D_CHECK(cudaStreamSynchronize(st));
+    return H3D_OK;
+}
+
+static int set_equalize_smem(size_t eq_smem) {
+    H3D_CHECK(cudaFuncSetAttribute(equalize_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eq_smem));
+    H3D_CHECK(cudaFuncSetAttribute(equalize_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eq_smem));
+    H3D_CHECK(cudaFuncSetAttribute(equalize_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eq_smem));
+    H3D_CHECK(cudaFuncSetAttribute(equalize_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eq_smem));
+    return H3D_OK;
+}
+
+#define DISPATCH_RC(CALL)                       \
+    if (max_rc <= 2) { CALL(2); }               \
+    else if (max_rc <= 4) { CALL(4); }          \
+    else if (max_rc <= 8) { CALL(8); }          \
+    else { CALL(16); }
+
 extern "C" size_t h3d_estimate_dispersion_ws_bytes(long long n_px, int n_seg, int n_reps, int n_conds) {
     const long long max_chunks = n_px / kChunk + n_seg + 1;
     size_t b = 0;
     b += ws_pad((size_t)n_reps * n_conds * n_px * 8);               // pseudo (worst case)
-    b += 2 * ws_pad((size_t)n_conds * max_chunks * 8);               // partials
     b += ws_pad((size_t)max_chunks * 4) + ws_pad((size_t)max_chunks * 8);
-    b += ws_pad((size_t)(n_seg + 1) * 8) + ws_pad((size_t)(n_seg + 1) * 4);
+    b += ws_pad((size_t)(n_seg + 1) * 8);
     b += ws_pad((size_t)n_seg * n_conds * sizeof(Problem));
+    b += ws_pad((size_t)n_seg * n_conds * sizeof(Fix128));
     b += ws_pad((size_t)n_seg * n_conds * 8) + ws_pad(64) + ws_pad(64);
     return b;
+}
+
+// rounds the host keeps queued ahead of the last round whose counters it has seen
+static int qcml_run_ahead() {
+    const char* e = getenv("H3D_QCML_AHEAD");
+    int v = e ? atoi(e) : 6;
+    return v < 1 ? 1 : (v > 64 ? 64 : v);
 }
 
 extern "C" int h3d_estimate_dispersion(const double* x, const double* f, long long ld,
@@ -573,18 +730,8 @@ extern "C" int h3d_estimate_dispersion(const double* x, const double* f, long lo
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned long long launches_before = h3d_launch_count();
     CondReps cr;
-    cr.n_conds = n_conds;
     int rows = 0, max_rc = 0;
-    for (int c = 0; c < H3D_MAX_CONDS; ++c) {
-        cr.n_in[c] = 0; cr.pseudo_row[c] = rows;
-        for (int k = 0; k < H3D_MAX_REPS; ++k) cr.rep[c][k] = 0;
-        if (c >= n_conds) continue;
-        for (int r = 0; r < n_reps; ++r)
-            if (design_host[r * n_conds + c]) cr.rep[c][cr.n_in[c]++] = r;
-        H3D_REQUIRE(cr.n_in[c] >= 1, "condition without replicates");
-        rows += cr.n_in[c];
-        if (cr.n_in[c] > max_rc) max_rc = cr.n_in[c];
-    }
+    { int rc = make_cond_reps(design_host, n_reps, n_conds, &cr, &rows, &max_rc); if (rc) return rc; }
     const long long n_px = seg_start_host[n_seg] - seg_start_host[0];
     H3D_REQUIRE(seg_start_host[0] == 0 && n_px <= ld, "segments must start at 0 and fit in ld");
     const int n_prob = n_seg * n_conds;
@@ -592,155 +739,147 @@ extern "C" int h3d_estimate_dispersion(const double* x, const double* f, long lo
     if (stats_host) for (int k = 0; k < 9; ++k) stats_host[k] = 0;
     if (n_px == 0) return H3D_OK;
 
-    // chunk tables (host)
-    const long long n_chunks_ll = count_chunks(seg_start_host, n_seg);
-    H3D_REQUIRE(n_chunks_ll < 2147483647LL, "too many chunks");
-    const int n_chunks = (int)n_chunks_ll;
-    std::vector<int> h_chunk_seg(n_chunks), h_seg_chunk_start(n_seg + 1);
-    std::vector<long long> h_chunk_lo(n_chunks);
-    int k = 0;
-    for (int s = 0; s < n_seg; ++s) {
-        h_seg_chunk_start[s] = k;
-        for (long long lo = seg_start_host[s]; lo < seg_start_host[s + 1]; lo += kChunk) {
-            h_chunk_seg[k] = s; h_chunk_lo[k] = lo; ++k;
-        }
-    }
-    h_seg_chunk_start[n_seg] = k;
-
     Workspace w(ws, ws_bytes);
+    ChunkTables ct;
+    { int rc = make_chunk_tables(seg_start_host, n_seg, w, st, &ct); if (rc) return rc; }
+    const int n_chunks = ct.n_chunks;
     double* pseudo = w.take<double>((size_t)rows * ld);
-    double* partial = w.take<double>((size_t)n_conds * n_chunks);
-    double* partial_cnt = w.take<double>((size_t)n_conds * n_chunks);
-    int* chunk_seg = w.take<int>(n_chunks);
-    long long* chunk_lo = w.take<long long>(n_chunks);
-    long long* seg_start = w.take<long long>(n_seg + 1);
-    int* seg_chunk_start = w.take<int>(n_seg + 1);
     Problem* prob = w.take<Problem>(n_prob);
+    Fix128* acc = w.take<Fix128>(n_prob);
     double* disp_dev = w.take<double>(n_prob);
     Counters* cnt = w.take<Counters>(1);
     long long* stats_dev = w.take<long long>(4);
-    if ( !partial || !partial_cnt || !chunk_seg || !chunk_lo || !seg_start ||
-        !seg_chunk_start || !prob || !disp_dev || !cnt || !stats_dev) {
+    if (!pseudo || !prob || !acc || !disp_dev || !cnt || !stats_dev) {
         set_error("estimate_dispersion workspace too small (%zu bytes given)", ws_bytes);
         return H3D_ERR_WORKSPACE;
     }
-    H3D_CHECK(cudaMemcpyAsync(chunk_seg, h_chunk_seg.data(), (size_t)n_chunks * 4, cudaMemcpyHostToDevice, st));
-    H3D_CHECK(cudaMemcpyAsync(chunk_lo, h_chunk_lo.data(), (size_t)n_chunks * 8, cudaMemcpyHostToDevice, st));
-    H3D_CHECK(cudaMemcpyAsync(seg_start, seg_start_host, (size_t)(n_seg + 1) * 8, cudaMemcpyHostToDevice, st));
-    H3D_CHECK(cudaMemcpyAsync(seg_chunk_start, h_seg_chunk_start.data(), (size_t)(n_seg + 1) * 4, cudaMemcpyHostToDevice, st));
-    // the host vectors must outlive the async copies
-    H3D_CHECK(cudaStreamSynchronize(st));
+    H3D_CHECK(cudaMemsetAsync(acc, 0, (size_t)n_prob * sizeof(Fix128), st));
 
     const int pgrid = div_up(n_prob, 128);
-    init_problems_kernel<<<pgrid, 128, 0, st>>>(prob, seg_start, n_seg, n_conds, estimator, cnt);
+    init_problems_kernel<<<pgrid, 128, 0, st>>>(prob, ct.seg_start, n_seg, n_conds, estimator, cnt);
     H3D_LAUNCHED("init_problems_kernel");
     const dim3 cgrid(n_chunks, n_conds);
-    Counters h_cnt;
+    const int ahead = qcml_run_ahead();
+    const int ring = 2 * ahead;
     void *pin_host = nullptr, *pin_dev = nullptr;
+    const size_t ring_bytes = (size_t)ring * sizeof(RoundSlot);
+    const size_t off_stats = (ring_bytes + 255) & ~(size_t)255, off_disp = off_stats + 256;
     {
-        int rc = pinned_scratch(256 + (size_t)n_prob * 8 + 64, &pin_host, &pin_dev);
+        int rc = pinned_scratch(off_disp + (size_t)n_prob * 8 + 64, &pin_host, &pin_dev);
         if (rc) return rc;
     }
-    static_assert(sizeof(Counters) == 16, "Counters is published as two 8-byte words");
+    volatile RoundSlot* ring_host = (volatile RoundSlot*)pin_host;
+    RoundSlot* ring_dev = (RoundSlot*)pin_dev;
+    for (int k = 0; k < ring; ++k) ring_host[k].seq = 0;     // nothing of an earlier call is in flight
     const size_t eq_smem = (size_t)kEqTasks * (sizeof(EqTask) + sizeof(int));
-    H3D_CHECK(cudaFuncSetAttribute(equalize_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eq_smem));
-    H3D_CHECK(cudaFuncSetAttribute(equalize_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eq_smem));
-    H3D_CHECK(cudaFuncSetAttribute(equalize_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eq_smem));
-    H3D_CHECK(cudaFuncSetAttribute(equalize_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eq_smem));
+    { int rc = set_equalize_smem(eq_smem); if (rc) return rc; }
     // per-kernel device time of the two heavy kernels (CUDA events on the
-    // launching stream; read after the synchronisation each iteration does)
-    cudaEvent_t ev[4];
-    for (int k = 0; k < 4; ++k) H3D_CHECK(cudaEventCreate(&ev[k]));
+    // launching stream, read once the round's counters have arrived)
+    EventPool evp;
+    { int rc = evp.create(4 * ring); if (rc) return rc; }
     double eq_us = 0.0, nll_us = 0.0;
     long long eq_launches = 0, nll_launches = 0;
 
-#define DISPATCH_RC(CALL)                       \
-    if (max_rc <= 2) { CALL(2); }               \
-    else if (max_rc <= 4) { CALL(4); }          \
-    else if (max_rc <= 8) { CALL(8); }          \
-    else { CALL(16); }
-
     if (estimator == H3D_EST_MME) {
-#define CALL(M) mme_kernel<M><<<cgrid, 256, 0, st>>>(x, f, ld, chunk_seg, chunk_lo, seg_start, cr, \
-        partial, partial_cnt, n_chunks)
+#define CALL(M) mme_kernel<M><<<cgrid, 256, 0, st>>>(x, f, ld, ct.chunk_seg, ct.chunk_lo, ct.seg_start, cr, acc)
         DISPATCH_RC(CALL)
 #undef CALL
         H3D_LAUNCHED("mme_kernel");
-        step_kernel<<<pgrid, 128, 0, st>>>(prob, seg_chunk_start, partial, partial_cnt, n_chunks, n_seg,
-                                           n_conds, estimator, 2, cnt);
+        step_kernel<<<pgrid, 128, 0, st>>>(prob, acc, n_prob, estimator, 2, cnt);
         H3D_LAUNCHED("step_kernel");
     } else {
-        int guard = 0;
-        bool need_eq = true;
-        while (true) {
-            const bool did_eq = need_eq;
-            if (need_eq) {
+        // Rounds of [pseudo-data for the bins that wait for it | likelihood of
+        // every searching bin at its current abscissa | Brent / fixed-point
+        // update | counters to the host].  Every kernel skips the bins that are
+        // not in the matching state, so a round queued after the last useful
+        // one is a no-op: the host keeps ``ahead`` rounds queued and reads the
+        // counters of finished rounds from mapped memory WITHOUT synchronising
+        // the stream (one host-device round trip per round was 2.4 ms of a
+        // 149 ms step, and 13 % of an 8-GPU step).
+        int launched = 0, seen = 0;
+        bool done = false;
+        int prev_need_eq = 1;                 // the first round computes pseudo-data
+        int err = H3D_OK;
+        while (!done) {
+            while (launched - seen < ahead) {
+                cudaEvent_t* ev = &evp.ev[4 * (launched % ring)];
                 H3D_CHECK(cudaEventRecord(ev[0], st));
-#define CALL(M) equalize_kernel<M><<<cgrid, 256, eq_smem, st>>>(x, f, ld, chunk_seg, chunk_lo, seg_start, cr, \
+#define CALL(M) equalize_kernel<M><<<cgrid, 256, eq_smem, st>>>(x, f, ld, ct.chunk_seg, ct.chunk_lo, ct.seg_start, cr, \
         estimator, prob, pseudo, cnt)
                 DISPATCH_RC(CALL)
 #undef CALL
                 H3D_LAUNCHED("equalize_kernel");
                 H3D_CHECK(cudaEventRecord(ev[1], st));
-                step_kernel<<<pgrid, 128, 0, st>>>(prob, seg_chunk_start, partial, partial_cnt, n_chunks,
-                                                   n_seg, n_conds, estimator, 0, cnt);
-                H3D_LAUNCHED("step_kernel");
-            }
-            H3D_CHECK(cudaEventRecord(ev[2], st));
-#define CALL(M) nll_kernel<M><<<cgrid, 256, 0, st>>>(pseudo, ld, chunk_seg, chunk_lo, seg_start, cr, prob, \
-        partial, n_chunks)
-            DISPATCH_RC(CALL)
+#define CALL(M) nll_kernel<M><<<cgrid, 256, 0, st>>>(pseudo, ld, ct.chunk_seg, ct.chunk_lo, ct.seg_start, cr, prob, acc)
+                DISPATCH_RC(CALL)
 #undef CALL
-            H3D_LAUNCHED("nll_kernel");
-            H3D_CHECK(cudaEventRecord(ev[3], st));
-            reset_counters_kernel<<<1, 1, 0, st>>>(cnt);
-            H3D_LAUNCHED("reset_counters_kernel");
-            step_kernel<<<pgrid, 128, 0, st>>>(prob, seg_chunk_start, partial, partial_cnt, n_chunks, n_seg,
-                                               n_conds, estimator, 1, cnt);
-            H3D_LAUNCHED("step_kernel");
-            publish_words_kernel<<<1, 32, 0, st>>>((const unsigned long long*)cnt,
-                                                   (volatile unsigned long long*)pin_dev, 2);
-            H3D_LAUNCHED("publish_words_kernel");
-            H3D_CHECK(cudaStreamSynchronize(st));
-            memcpy(&h_cnt, pin_host, sizeof(Counters));
+                H3D_LAUNCHED("nll_kernel");
+                H3D_CHECK(cudaEventRecord(ev[2], st));
+                step_kernel<<<pgrid, 128, 0, st>>>(prob, acc, n_prob, estimator, 1, cnt);
+                H3D_LAUNCHED("step_kernel");
+                publish_round_kernel<<<1, 1, 0, st>>>(cnt, ring_dev + (launched % ring),
+                                                     (unsigned long long)launched + 1ull);
+                H3D_LAUNCHED("publish_round_kernel");
+                ++launched;
+                if (launched > 200000) break;
+            }
+            // counters of round ``seen``
+            volatile RoundSlot* slot = ring_host + (seen % ring);
+            long long spins = 0;
+            while (slot->seq != (unsigned long long)seen + 1ull) {
+                if ((++spins & 0xffff) == 0) {
+                    const cudaError_t qe = cudaStreamQuery(st);
+                    if (qe != cudaSuccess && qe != cudaErrorNotReady) {
+                        set_error("qCML round %d: %s", seen, cudaGetErrorString(qe));
+                        return H3D_ERR_CUDA;
+                    }
+                    if (qe == cudaSuccess && slot->seq != (unsigned long long)seen + 1ull) {
+                        set_error("qCML round %d finished without publishing its counters", seen);
+                        return H3D_ERR_CUDA;
+                    }
+                }
+            }
+            __sync_synchronize();
+            const int n_need_eq = slot->n_need_eq, n_in_brent = slot->n_in_brent;
+            const int n_failed = slot->n_failed, n_fit_failed = slot->n_fit_failed;
             {
+                cudaEvent_t* ev = &evp.ev[4 * (seen % ring)];
                 float ms = 0.f;
-                if (did_eq) {
+                if (prev_need_eq) {
                     H3D_CHECK(cudaEventElapsedTime(&ms, ev[0], ev[1]));
                     eq_us += 1e3 * (double)ms; ++eq_launches;
                 }
-                H3D_CHECK(cudaEventElapsedTime(&ms, ev[2], ev[3]));
+                H3D_CHECK(cudaEventElapsedTime(&ms, ev[1], ev[2]));
                 nll_us += 1e3 * (double)ms; ++nll_launches;
             }
-            if (h_cnt.n_failed > 0) {
+            ++seen;
+            prev_need_eq = n_need_eq > 0;
+            if (n_failed > 0) {
                 set_error("bounded Brent search failed for %d (distance, condition) bins "
-                          "(NaN likelihood or evaluation budget exhausted)", h_cnt.n_failed);
-                return H3D_ERR_NUMERIC;
+                          "(NaN likelihood or evaluation budget exhausted)", n_failed);
+                err = H3D_ERR_NUMERIC; break;
             }
-            if (h_cnt.n_fit_failed > 0) {
-                set_error("fit_mu_hat: %d pixels with all-zero counts inside a condition",
-                          h_cnt.n_fit_failed);
-                return H3D_ERR_NUMERIC;
+            if (n_fit_failed > 0) {
+                set_error("fit_mu_hat: %d pixels with all-zero counts inside a condition", n_fit_failed);
+                err = H3D_ERR_NUMERIC; break;
             }
-            need_eq = h_cnt.n_need_eq > 0;
-            if (!need_eq && h_cnt.n_in_brent == 0) break;
-            if (++guard > 100000) { set_error("qCML did not terminate"); return H3D_ERR_NUMERIC; }
+            if (n_need_eq == 0 && n_in_brent == 0) done = true;
+            else if (seen > 200000) { set_error("qCML did not terminate"); err = H3D_ERR_NUMERIC; break; }
         }
+        if (err != H3D_OK) { cudaStreamSynchronize(st); return err; }
     }
-    for (int k = 0; k < 4; ++k) cudaEventDestroy(ev[k]);
     collect_kernel<<<1, 256, 0, st>>>(prob, n_prob, disp_dev, stats_dev);
     H3D_LAUNCHED("collect_kernel");
-    // disp_dev and stats_dev are adjacent 256-byte aligned carvings: publish both
     publish_words_kernel<<<1, 256, 0, st>>>((const unsigned long long*)disp_dev,
-                                            (volatile unsigned long long*)((char*)pin_dev + 256), n_prob);
+                                            (volatile unsigned long long*)((char*)pin_dev + off_disp), n_prob);
     H3D_LAUNCHED("publish_words_kernel");
     publish_words_kernel<<<1, 32, 0, st>>>((const unsigned long long*)stats_dev,
-                                           (volatile unsigned long long*)((char*)pin_dev + 64), 4);
+                                           (volatile unsigned long long*)((char*)pin_dev + off_stats), 4);
     H3D_LAUNCHED("publish_words_kernel");
-    H3D_CHECK(cudaStreamSynchronize(st));
-    memcpy(disp_per_dist_host, (char*)pin_host + 256, (size_t)n_prob * 8);
+    H3D_CHECK(cudaStreamSynchronize(st));       // also drains the queued no-op rounds
+    memcpy(disp_per_dist_host, (char*)pin_host + off_disp, (size_t)n_prob * 8);
     long long h_stats[4] = {0, 0, 0, 0};
-    memcpy(h_stats, (char*)pin_host + 64, 4 * sizeof(long long));
+    memcpy(h_stats, (char*)pin_host + off_stats, 4 * sizeof(long long));
     if (stats_host) {
         stats_host[0] = h_stats[0]; stats_host[1] = h_stats[1]; stats_host[2] = h_stats[2];
         stats_host[3] = (long long)(h3d_launch_count() - launches_before);
@@ -748,5 +887,49 @@ extern "C" int h3d_estimate_dispersion(const double* x, const double* f, long lo
         stats_host[6] = nll_launches; stats_host[7] = (long long)nll_us;
         stats_host[8] = h_stats[3];
     }
+    return H3D_OK;
+}
+
+// Pseudo-data of ONE bin at a given dispersion: hic3defdr/util/scaled_nb.py:
+// 186-214 (equalize).  x, f: SoA (n_reps, ld), every replicate belongs to the
+// one condition; pseudo_out: SoA (n_reps, ld).  The same kernel the qCML
+// driver launches; exposed so that the device pseudo-data can be compared
+// element by element with the reference's.
+extern "C" size_t h3d_equalize_ws_bytes(long long n_px) {
+    const long long max_chunks = n_px / kChunk + 2;
+    return ws_pad((size_t)max_chunks * 4) + ws_pad((size_t)max_chunks * 8) + ws_pad(16) +
+           ws_pad(sizeof(Problem)) + ws_pad(64);
+}
+
+extern "C" int h3d_equalize(const double* x, const double* f, long long ld, long long n_px, int n_reps,
+                            double alpha, double* pseudo_out, int* n_fit_failed, void* ws,
+                            size_t ws_bytes, h3d_stream_t stream) {
+    H3D_REQUIRE(n_reps >= 1 && n_reps <= H3D_MAX_REPS, "n_reps out of range");
+    H3D_REQUIRE(n_px >= 0 && n_px <= ld, "n_px must fit in ld");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_px == 0) return H3D_OK;
+    std::vector<unsigned char> design(n_reps, 1);
+    CondReps cr;
+    int rows = 0, max_rc = 0;
+    { int rc = make_cond_reps(design.data(), n_reps, 1, &cr, &rows, &max_rc); if (rc) return rc; }
+    const long long seg[2] = {0, n_px};
+    Workspace w(ws, ws_bytes);
+    ChunkTables ct;
+    { int rc = make_chunk_tables(seg, 1, w, st, &ct); if (rc) return rc; }
+    Problem* prob = w.take<Problem>(1);
+    Counters* cnt = w.take<Counters>(1);
+    if (!prob || !cnt) { set_error("equalize workspace too small (%zu bytes given)", ws_bytes); return H3D_ERR_WORKSPACE; }
+    single_bin_problems_kernel<<<1, 32, 0, st>>>(prob, 1, n_px, alpha, cnt);
+    H3D_LAUNCHED("single_bin_problems_kernel");
+    const size_t eq_smem = (size_t)kEqTasks * (sizeof(EqTask) + sizeof(int));
+    { int rc = set_equalize_smem(eq_smem); if (rc) return rc; }
+    const dim3 cgrid(ct.n_chunks, 1);
+#define CALL(M) equalize_kernel<M><<<cgrid, 256, eq_smem, st>>>(x, f, ld, ct.chunk_seg, ct.chunk_lo, ct.seg_start, cr, \
+        H3D_EST_QCML, prob, pseudo_out, cnt)
+    DISPATCH_RC(CALL)
+#undef CALL
+    H3D_LAUNCHED("equalize_kernel");
+    if (n_fit_failed)
+        H3D_CHECK(cudaMemcpyAsync(n_fit_failed, &cnt->n_fit_failed, sizeof(int), cudaMemcpyDeviceToDevice, st));
     return H3D_OK;
 }

@@ -530,9 +530,13 @@ H3D_HD double q2q_one(double x, double mu_in, double mu_out, double alpha) {
         const GammaShape s_in = gamma_shape(a_in);
         double lt, ratio, lk;
         gamma_log_tail(s_in, xs, right, &lt, &ratio, &lk);
-        // cephes igam/igamc flush to zero when the kernel x^a e^-x / Gamma(a)
-        // underflows exp(-MAXLOG)
-        if (lk < -709.782712893384 || lt < -744.44) {
+        // scipy's igam / igamc (cephes igam_fac) return 0 when the kernel
+        // x^a e^-x / Gamma(a) is below exp(-MAXLOG) -- but only on their
+        // "far" branch |a - x| > 0.4 a; closer to the mode the kernel is formed
+        // as a product that keeps denormal values, and the tail probability
+        // only vanishes where it underflows the double range itself
+        const bool far = fabs(a_in - xs) > 0.4 * a_in;
+        if ((far && lk < -709.782712893384) || lk < -744.44 || lt < -744.44) {
             q_gamma = right ? INFINITY : 0.0;            // sf / cdf underflow in the reference
         } else {
             double guess = xs * (a_out / a_in);

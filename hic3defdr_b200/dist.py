@@ -30,8 +30,25 @@ import torch
 import torch.distributed as td
 
 
+import contextlib
+
+_SINGLE = [False]
+
+
+@contextlib.contextmanager
+def single_process():
+    """Inside this context the calling process behaves as a one-process run
+    even though a process group exists (no collectives are issued): used to
+    recompute a result on one rank for comparison with the sharded run."""
+    _SINGLE[0] = True
+    try:
+        yield
+    finally:
+        _SINGLE[0] = False
+
+
 def initialized():
-    return td.is_available() and td.is_initialized()
+    return td.is_available() and td.is_initialized() and not _SINGLE[0]
 
 
 def rank():
@@ -45,6 +62,18 @@ def world_size():
 def barrier():
     if initialized() and world_size() > 1:
         td.barrier()
+
+
+def broadcast_flags(flags):
+    """rank 0's list of booleans on every rank (decisions that guard code
+    containing collectives must be the same everywhere)"""
+    if not (initialized() and world_size() > 1):
+        return [bool(v) for v in flags]
+    t = torch.tensor([int(bool(v)) for v in flags], dtype=torch.int64)
+    if td.get_backend() == 'nccl':
+        t = t.cuda()
+    td.broadcast(t, src=0)
+    return [bool(v) for v in t.cpu().tolist()]
 
 
 def lpt_assign(weights, n_ranks):

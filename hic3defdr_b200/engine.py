@@ -37,13 +37,7 @@ def prepare_chrom_steps(csr, bias_raw, design, dist_min=4, dist_max=200,
     u = ops.union_emit(csr, dist_max, bias, offs, n_px)
     st = dict(bias=bias, row=u['row'], col=u['col'], raw=u['raw'])
     if n_px == 0:
-        r = csr.n_reps
-        st.update(size_factors=torch.empty((0, r), dtype=torch.float64,
-                                           device='cuda'),
-                  scaled=u['balanced'],
-                  disp_idx=torch.empty(0, dtype=torch.uint8, device='cuda'),
-                  disp_index=torch.empty(0, dtype=torch.int32, device='cuda'))
-        return st
+        return _empty_prepared(st, csr.n_reps, u['balanced'], loop_pixels)
     table = ops.size_factor_table(u['balanced'], u['dist'], dist_max, n_bins,
                                   norm)
     scaled, sf, disp_idx = ops.scale_filter(
@@ -71,12 +65,16 @@ def prepare_chrom(csr, bias_raw, design, *args, **kw):
         return stop.value
 
 
-def _empty_prepared(st, n_reps, balanced):
+def _empty_prepared(st, n_reps, balanced, loop_pixels=None):
     st.update(size_factors=torch.empty((0, n_reps), dtype=torch.float64,
                                        device='cuda'),
               scaled=balanced,
               disp_idx=torch.empty(0, dtype=torch.uint8, device='cuda'),
               disp_index=torch.empty(0, dtype=torch.int32, device='cuda'))
+    if loop_pixels is not None:
+        # every rank must hold the same set of arrays: the sharded writers
+        # (analysis._save_sharded) run one collective per array
+        st['loop_idx'] = torch.empty(0, dtype=torch.uint8, device='cuda')
     return st
 
 
@@ -101,10 +99,10 @@ def prepare_chrom_sharded(csr, bias_raw, design, dist_min=4, dist_max=200,
                                             n_bins, norm)
     if n_px == 0 or table is None:
         if 'conditional' not in norm and table is not None:
-            _empty_prepared(st, csr.n_reps, u['balanced'])
+            _empty_prepared(st, csr.n_reps, u['balanced'], loop_pixels)
             st['size_factors'] = table
             return st
-        return _empty_prepared(st, csr.n_reps, u['balanced'])
+        return _empty_prepared(st, csr.n_reps, u['balanced'], loop_pixels)
     scaled, sf, disp_idx = ops.scale_filter(
         u['row'], u['col'], u['balanced'], table, design, dist_max,
         mean_thresh, dist_min)
@@ -172,7 +170,7 @@ def prepare_many(chrom_inputs, design, n_streams=None, sink=None, **kw):
     return [states[i] for i in sorted(states)]
 
 
-def pool_by_distance(states, dist_max):
+def pool_by_distance(states, dist_max, n_reps=None):
     """Pools the disp_idx pixels of the given chromosomes by distance
     (analysis/analysis.py:169-183, 196-197): returns (x, f) SoA (R, n) in
     (distance key, chromosome, row, col) order, the per-pixel distances in
@@ -183,7 +181,11 @@ def pool_by_distance(states, dist_max):
     counts = [int(s['disp_index'].numel()) for s in states]
     offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
     n_tot = int(offs[-1])
-    n_reps = states[0]['raw'].shape[1] if states else 1
+    if n_reps is None:
+        # a rank without chromosomes must still take part in the exchange with
+        # the same number of replicate rows as the others: callers that may run
+        # multi-process pass the design's replicate count
+        n_reps = states[0]['raw'].shape[1] if states else 1
     dist_cat = torch.empty(n_tot, dtype=torch.int32, device='cuda')
     for s, o, n in zip(states, offs[:-1], counts):
         if s['size_factors'].dim() != 2:
@@ -267,6 +269,30 @@ def fit_trends(disp_per_dist, dist_max, cond_names, frac=None,
     return fns, table
 
 
+def _estimate_with_callable(x, f, seg_start, design, estimator):
+    """analysis/analysis.py:164-165, 186-206 with a user-supplied Python
+    estimator ``(data (pixels, replicates), f=...) -> float``: the pooled
+    pixels of every (distance, condition) bin are handed to it on the host, as
+    the reference does; everything around it (pooling, exchange, trend, gather)
+    stays on the device."""
+    xs, fs = x.cpu().numpy(), f.cpu().numpy()
+    n_seg = len(seg_start) - 1
+    out = np.full((n_seg, design.shape[1]), np.nan)
+    for s in range(n_seg):
+        lo, hi = int(seg_start[s]), int(seg_start[s + 1])
+        if hi == lo:
+            continue
+        for c in range(design.shape[1]):
+            reps = np.flatnonzero(design[:, c])
+            raw_slice = np.ascontiguousarray(xs[reps, lo:hi].T).astype(np.int64)
+            f_slice = np.ascontiguousarray(fs[reps, lo:hi].T)
+            out[s, c] = estimator(raw_slice, f=f_slice)
+    return out, dict(outer_iterations=0, nll_evaluations=0,
+                     pixel_equalizations=0, launches=0, equalize_launches=0,
+                     equalize_us=0, nll_launches=0, nll_us=0,
+                     capped_segments=0)
+
+
 def estimate_disp(states, design, dist_max, cond_names=None, estimator='qcml',
                   frac=None, auto_frac_factor=15., weighted_lowess=True,
                   log=None):
@@ -277,14 +303,19 @@ def estimate_disp(states, design, dist_max, cond_names=None, estimator='qcml',
     if cond_names is None:
         cond_names = [str(c) for c in range(n_conds)]
     with stage('estimate_disp/pool'):
-        x, f, dist_cat, seg_start, offs = pool_by_distance(states, dist_max)
+        x, f, dist_cat, seg_start, offs = pool_by_distance(
+            states, dist_max, n_reps=design.shape[0])
     n_tot = int(offs[-1])
     # multi-GPU: every distance is estimated on the rank that owns it
     with stage('estimate_disp/exchange'):
         x, f, seg_start = hdist.exchange_by_distance(x, f, seg_start, n_tot)
     with stage('estimate_disp/qcml'):
-        disp_per_dist, stats = ops.estimate_dispersion(x, f, seg_start, design,
-                                                       estimator)
+        if callable(estimator):
+            disp_per_dist, stats = _estimate_with_callable(
+                x, f, seg_start, design, estimator)
+        else:
+            disp_per_dist, stats = ops.estimate_dispersion(
+                x, f, seg_start, design, estimator)
     with stage('estimate_disp/merge'):
         disp_per_dist = hdist.merge_disp_per_dist(disp_per_dist, dist_max + 1)
     del x, f

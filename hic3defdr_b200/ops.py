@@ -475,6 +475,24 @@ def estimate_dispersion(x_soa, f_soa, seg_start, design, estimator='qcml'):
                      capped_segments=int(stats[8]))
 
 
+def equalize(data, f, alpha):
+    """hic3defdr/util/scaled_nb.py:186-214: pseudo-data of one bin, (n, R)
+    counts and factors, scalar dispersion -> (n, R) float64 CUDA tensor."""
+    data = np.asarray(data.cpu() if isinstance(data, torch.Tensor) else data,
+                      dtype=float)
+    n, r = data.shape
+    x = dev(np.ascontiguousarray(data.T))
+    fd = dev(np.ascontiguousarray(np.asarray(f, dtype=float).T))
+    out = torch.empty((r, max(n, 1)), dtype=torch.float64, device='cuda')
+    failed = torch.zeros(1, dtype=torch.int32, device='cuda')
+    wsb = lib().query('h3d_equalize_ws_bytes', n)
+    ws = workspace(wsb)
+    lib().call('h3d_equalize', ptr(x), ptr(fd), max(n, 1), n, r, float(alpha),
+               ptr(out), ptr(failed), ptr(ws), wsb, _stream())
+    _check_failed(failed, 'equalize')
+    return out[:, :n].t().contiguous()
+
+
 def _single_bin(data, f, estimator):
     data = np.asarray(data.cpu() if isinstance(data, torch.Tensor) else data,
                       dtype=float)

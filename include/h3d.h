@@ -202,7 +202,11 @@ size_t h3d_stable_rank_ws_bytes(long long n, int n_keys);
  * cycles forever where the dispersion is large and the bin small (the bounded
  * Brent search resolves delta to 1e-5, i.e. disp = delta / (1 - delta) only
  * to ~0.05 at disp ~ 66).  Here a segment stops after H3D_QCML_MAX_OUTER
- * outer iterations with its last iterate, and is counted in stats[8]. */
+ * outer iterations with its last iterate, and is counted in stats[8].
+ * The likelihood of a bin is summed in 128-bit fixed point, i.e. exactly: the
+ * result does not depend on the order of the pixels inside a segment (nor,
+ * therefore, on how many GPUs pooled them).  The host queues
+ * H3D_QCML_AHEAD (environment, default 6) rounds ahead of the device. */
 #define H3D_QCML_MAX_OUTER 100
 #define H3D_EST_QCML 0
 #define H3D_EST_CML 1
@@ -215,6 +219,17 @@ int h3d_estimate_dispersion(const double* x, const double* f, long long ld,
                             void* ws, size_t ws_bytes, h3d_stream_t stream);
 size_t h3d_estimate_dispersion_ws_bytes(long long n_px, int n_seg, int n_reps,
                                         int n_conds);
+
+/* equalize, hic3defdr/util/scaled_nb.py:186-214 (with q2qnbinom, :217-275):
+ * pseudo-data of ONE bin at dispersion ``alpha``.  x, f: SoA (n_reps, ld),
+ * all replicates of one condition; pseudo_out: SoA (n_reps, ld).  The very
+ * kernel the qCML driver launches, exposed so that the device pseudo-data can
+ * be checked element by element.  n_fit_failed (device int32, may be NULL):
+ * number of pixels with all-zero counts (the reference raises there). */
+int h3d_equalize(const double* x, const double* f, long long ld, long long n_px,
+                 int n_reps, double alpha, double* pseudo_out, int* n_fit_failed,
+                 void* ws, size_t ws_bytes, h3d_stream_t stream);
+size_t h3d_equalize_ws_bytes(long long n_px);
 
 /* lowess (lib5c.util.lowess.lowess as called at hic3defdr/util/lowess.py:72):
  * x sorted ascending, n points, returns fitted values y_fit (device). */

@@ -1,6 +1,7 @@
 """
 TEST INFRASTRUCTURE -- imports the UNMODIFIED reference from /root/reference in
-the build container (it does not exist on the GPU box) so that
+the build container (on the GPU box: from the copy under oracle/_ref that
+``__graft_entry__.build()`` makes; it is git-ignored, never committed) so that
 tests/golden/make_golden.py can record its outputs as fixtures and so that the
 restatement in oracle/pipeline.py can be validated against the real thing.
 
@@ -22,7 +23,22 @@ import sys
 import types
 from unittest import mock
 
-REFERENCE_ROOT = os.environ.get('H3D_REFERENCE_ROOT', '/root/reference')
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_reference():
+    """/root/reference in the build container; on the GPU box the copy of the
+    (pure-Python) package that ``__graft_entry__.build()`` placed under
+    oracle/_ref (git-ignored, travels like the built .so files)."""
+    env = os.environ.get('H3D_REFERENCE_ROOT')
+    for root in ([env] if env else []) + ['/root/reference',
+                                          os.path.join(_HERE, '_ref')]:
+        if os.path.isdir(os.path.join(root, 'hic3defdr')):
+            return root
+    return env or '/root/reference'
+
+
+REFERENCE_ROOT = _find_reference()
 
 _STUB_PREFIXES = (
     'matplotlib', 'seaborn', 'mpl_scatter_density', 'lib5c.plotters',

@@ -1,0 +1,157 @@
+"""GPU parity at full size: BASELINE.json configs[0] (chr18 + chr19 mouse-sized
+at 10 kb, 2-vs-2, dist cap 200: 2.8 M union pixels, 2.2 M tested) through the
+drop-in class, files in -> files out, against the run of the UNMODIFIED
+reference recorded in tests/golden/ref_config1.npz
+(tests/golden/make_golden_config1.py).
+
+Tolerances: union indices, raw, disp_idx bit-exact
+(checksums); size factors / scaled 1e-12; disp_per_dist 1e-7 (bins of ~11 k
+pixels: the reference's own summation-order noise is ~1e-9 there); end to end
+(device all the way) p / q / llr / mu_hat 1e-6 and an identical significant
+set except pixels whose q is within 1e-6 relative of the threshold."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sparse
+
+from tests.helpers import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+CHROMS = ('chr18', 'chr19')
+DIST_MAX = 200
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope='module')
+def run(tmp_path_factory):
+    from hic3defdr_b200 import HiC3DeFDR
+    from hic3defdr_b200.synth import MM10_10KB, write_dataset
+    g = np.load(os.path.join(GOLDEN, 'ref_config1.npz'))
+    root = str(tmp_path_factory.mktemp('config1'))
+    kw = write_dataset(root, {c: MM10_10KB[c] for c in CHROMS}, n_reps=4,
+                       dist_max=DIST_MAX, config=1, amp=300.0)
+    kw.pop('loop_patterns')
+    # the inputs must be the ones the reference saw
+    for c in CHROMS:
+        h = hashlib.sha256()
+        for pat in kw['raw_npz_patterns']:
+            m = sparse.load_npz(pat.replace('<chrom>', c)).tocsr()
+            for a in (m.indptr, m.indices, m.data):
+                h.update(np.ascontiguousarray(a).tobytes())
+        for pat in kw['bias_patterns']:
+            h.update(np.loadtxt(pat.replace('<chrom>', c)).tobytes())
+        assert h.hexdigest() == str(g['input_sha_%s' % c]), \
+            'synthetic generator drifted: regenerate tests/golden/ref_config1.npz'
+    outdir = os.path.join(root, 'out')
+    h = HiC3DeFDR(outdir=outdir, dist_thresh_max=DIST_MAX, **kw)
+    h.run_to_qvalues(n_threads=0)
+    return g, h, outdir
+
+
+def _ld(outdir, name, c):
+    return np.load(os.path.join(outdir, '%s_%s.npy' % (name, c)))
+
+
+def test_union_and_filters_bit_exact(run):
+    g, h, outdir = run
+    for c in CHROMS:
+        for name in ('row', 'col', 'raw', 'disp_idx'):
+            assert sha(_ld(outdir, name, c)) == str(g['sha_%s_%s' % (name, c)]), \
+                (name, c)
+        n, n_d = [int(v) for v in g['n_%s' % c]]
+        assert len(_ld(outdir, 'row', c)) == n
+        assert int(_ld(outdir, 'disp_idx', c).sum()) == n_d
+
+
+def test_size_factors_and_scaled(run):
+    g, h, outdir = run
+    for c in CHROMS:
+        sf = _ld(outdir, 'size_factors', c)
+        dist = _ld(outdir, 'col', c) - _ld(outdir, 'row', c)
+        want = g['sf_table_%s' % c][dist]
+        np.testing.assert_allclose(sf, want, rtol=1e-12)
+        di = _ld(outdir, 'disp_idx', c)
+        idx = g['sample_%s' % c]
+        np.testing.assert_array_equal(_ld(outdir, 'raw', c)[di][idx],
+                                      g['sample_raw_%s' % c])
+        np.testing.assert_allclose(_ld(outdir, 'scaled', c)[di][idx],
+                                   g['sample_scaled_%s' % c], rtol=1e-12)
+
+
+def test_dispersion_per_distance(run):
+    g, h, outdir = run
+    got = np.load(os.path.join(outdir, 'disp_per_dist.npy'))
+    want = g['disp_per_dist']
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    ok = np.isfinite(want)
+    err = np.abs(got[ok] - want[ok]) / want[ok]
+    print('config 1: disp_per_dist max relative difference %.2e' % err.max())
+    assert err.max() < 1e-7
+
+
+def _same_trend_branch(g, outdir):
+    """see tests/test_gpu_pipeline.py::_trend_branch_matches"""
+    from hic3defdr_b200.trend import point_multiplicities
+    got = np.load(os.path.join(outdir, 'disp_per_dist.npy'))
+    for c in range(2):
+        ok = np.isfinite(g['disp_per_dist'][:, c])
+        if not np.array_equal(
+                point_multiplicities(g['disp_per_dist'][:, c][ok])[0],
+                point_multiplicities(got[:, c][ok])[0]):
+            return False
+    return True
+
+
+def test_end_to_end_sample_and_significant_set(run):
+    g, h, outdir = run
+    xs = np.arange(DIST_MAX + 1, dtype=float)
+    same_branch = _same_trend_branch(g, outdir)
+    if not same_branch:
+        # the reference's point weighting is bistable in the last bit of a
+        # rolling variance ("Trend fit sensitivity"): compare with
+        # the oracle's continuation of OUR disp_per_dist instead
+        from oracle import pipeline as op
+        dpd = np.load(os.path.join(outdir, 'disp_per_dist.npy'))
+        fits = []
+        for c in range(2):
+            ok = np.isfinite(dpd[:, c])
+            fits.append(op.weighted_trend(xs[ok], dpd[:, c][ok],
+                                          left_boundary=dpd[:, c][ok][0]))
+        for c, cond in enumerate('AB'):
+            np.testing.assert_allclose(h.load_disp_fn(cond)(xs),
+                                       op.eval_trend(fits[c], xs), rtol=1e-9)
+        pytest.skip('run landed on the other branch of the reference\'s '
+                    'bistable trend weighting; trend checked stage-isolated')
+    for cond in 'AB':
+        np.testing.assert_allclose(h.load_disp_fn(cond)(xs),
+                                   g['disp_fn_%s' % cond], rtol=1e-6)
+    q_all, q_ref_n = [], g['n_sig']
+    for c in CHROMS:
+        idx = g['sample_%s' % c]
+        for name, tol in (('disp', 1e-6), ('mu_hat_null', 1e-6),
+                          ('mu_hat_alt', 1e-6)):
+            np.testing.assert_allclose(_ld(outdir, name, c)[idx],
+                                       g['%s_%s' % (name, c)], rtol=tol,
+                                       err_msg=name)
+        np.testing.assert_allclose(_ld(outdir, 'llr', c)[idx], g['llr_%s' % c],
+                                   rtol=1e-6, atol=1e-9)
+        p, wp = _ld(outdir, 'pvalues', c)[idx], g['pvalues_%s' % c]
+        good = -2 * g['llr_%s' % c] >= 1e-8
+        np.testing.assert_allclose(p[good], wp[good], rtol=1e-6)
+        q, wq = _ld(outdir, 'qvalues', c)[idx], g['qvalues_%s' % c]
+        np.testing.assert_allclose(q, wq, rtol=1e-6, atol=1e-300)
+        for fdr in (0.01, 0.05, 0.2):
+            near = np.abs(wq - fdr) <= 1e-6 * fdr
+            assert np.array_equal((q < fdr)[~near], (wq < fdr)[~near])
+        q_all.append(_ld(outdir, 'qvalues', c))
+    q = np.concatenate(q_all)
+    for fdr, n_ref in zip((0.01, 0.05, 0.2), q_ref_n):
+        n_near = int((np.abs(q - fdr) <= 1e-6 * fdr).sum())
+        assert abs(int((q < fdr).sum()) - int(n_ref)) <= n_near, fdr
+    assert float(q.sum()) == pytest.approx(float(g['q_sum']), rel=1e-7)

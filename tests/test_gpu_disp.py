@@ -184,3 +184,99 @@ def test_bh_buckets_equal_the_single_correction(n):
         carry = min(mins[b + 1:] + [np.inf])
         got[sel[b]] = ops.apply_bh_carry(qs[b], carry).cpu().numpy()
     assert np.array_equal(got, want, equal_nan=True)
+
+
+# --------------------------------------------------------------------------
+# device pseudo-data, element by element
+# --------------------------------------------------------------------------
+
+@pytest.mark.parametrize('alpha', [0.01, 0.2, 1e-3])
+def test_equalize_device_vs_recorded_reference_bin(alpha):
+    """h3d_equalize (the kernel the qCML driver launches) against the
+    reference's equalize on the recorded 1500-pixel bin, tolerance 1e-9
+    relative to max(value, 1e-3) (tests/test_hostcheck_math.py::check_pseudo)"""
+    from hic3defdr_b200 import ops
+    from tests.test_hostcheck_math import check_pseudo
+    s = load_stage_golden()
+    got = ops.equalize(s['bin_x'], s['bin_f'], alpha).cpu().numpy()
+    check_pseudo(got, s['equalize_%g' % alpha])
+
+
+def test_equalize_device_four_replicates():
+    from hic3defdr_b200 import ops
+    from tests.test_hostcheck_math import check_pseudo
+    s = load_stage_golden()
+    got = ops.equalize(s['bin4_x'], s['bin4_f'], 0.05).cpu().numpy()
+    check_pseudo(got, s['equalize4_0.05'])
+
+
+@pytest.mark.parametrize('case', ['small', 'tails', 'grid', 'three'])
+def test_equalize_device_vs_recorded_reference_edges(case):
+    """the reference's equalize recorded on edge cases
+    (tests/golden/make_golden_equalize.py): mu < 0.25 clamp, x = 0, both
+    tails up to the underflow of the tail probabilities (-> +inf / clipped to
+    0), series and continued-fraction branches, an odd replicate count; seven
+    dispersions from 1e-4 to 20"""
+    import os
+    from hic3defdr_b200 import ops
+    from tests.helpers import GOLDEN
+    from tests.test_hostcheck_math import check_pseudo
+    g = np.load(os.path.join(GOLDEN, 'ref_equalize_edges.npz'))
+    x, f = g['%s_x' % case], g['%s_f' % case]
+    worst = 0.0
+    for a in g['alphas']:
+        got = ops.equalize(x, f, float(a)).cpu().numpy()
+        worst = max(worst, check_pseudo(got, g['%s_%g' % (case, a)]))
+    print('equalize %s: worst relative error %.2e' % (case, worst))
+
+
+def test_equalize_raises_on_all_zero_pixel():
+    from hic3defdr_b200 import ops
+    with pytest.raises(AssertionError):
+        ops.equalize(np.array([[1, 2], [0, 0]]), np.ones((2, 2)), 0.01)
+
+
+def _pooled_golden():
+    from hic3defdr_b200 import ops
+    gold = load_pipeline_golden()
+    g = gold['g']
+    raws, fs, dists = [], [], []
+    for c, (mats, bias_raw) in zip(gold['chroms'], gold['inputs']):
+        di = g['disp_idx_%s' % c]
+        bias = op.filter_bias(bias_raw, 0.1)
+        r, cc = g['row_%s' % c][di], g['col_%s' % c][di]
+        raws.append(g['raw_%s' % c][di])
+        fs.append(op.combined_factor(bias, r, cc, g['size_factors_%s' % c][di]))
+        dists.append(cc - r)
+    return gold, np.concatenate(raws), np.concatenate(fs), \
+        np.concatenate(dists)
+
+
+@pytest.mark.parametrize('estimator', ['qcml', 'mme'])
+def test_estimate_is_independent_of_pixel_order(estimator):
+    """The likelihood (and the MME mean) of a bin is summed in 128-bit fixed
+    point: permuting the pixels inside every distance segment -- what pooling
+    over several GPUs does -- must not change a single bit of the result."""
+    from hic3defdr_b200 import ops
+    gold, raw, f, dist = _pooled_golden()
+    dmax = gold['dist_max']
+    rng = np.random.default_rng(5)
+    results = []
+    for trial in range(3):
+        order = np.arange(len(dist)) if trial == 0 else \
+            rng.permutation(len(dist))
+        d = dist[order]
+        rank, start = ops.stable_rank(d.astype(np.int32), dmax + 1)
+        rk = rank.cpu().numpy()
+        ld = len(d) + 7 * trial              # the leading dimension is free too
+        x_soa = np.zeros((raw.shape[1], ld))
+        f_soa = np.ones_like(x_soa)
+        x_soa[:, rk] = raw[order].T
+        f_soa[:, rk] = f[order].T
+        got, _ = ops.estimate_dispersion(ops.dev(x_soa), ops.dev(f_soa),
+                                         start.cpu().numpy(), gold['design'],
+                                         estimator)
+        results.append(got)
+    assert np.isfinite(results[0]).sum() > 50
+    np.testing.assert_array_equal(results[1], results[0])
+    np.testing.assert_array_equal(results[2], results[0])

@@ -147,7 +147,8 @@ def test_end_to_end_against_recorded_reference(run):
     the same branch of the reference's bistable trend fit (see above)."""
     gold, h, outdir = run
     g = gold['g']
-    if not _trend_branch_matches(gold, outdir):
+    same_branch = _trend_branch_matches(gold, outdir)
+    if not same_branch:
         # the recorded run is on the other branch of the reference's bistable
         # point weighting: the reference's answer for OUR dispersion estimates
         # is then the oracle's (bitwise restatement of the reference) unbroken
@@ -181,17 +182,35 @@ def test_end_to_end_against_recorded_reference(run):
             for k, v in want[c].items():
                 g['%s_%s' % (k, c)] = v
             g['qvalues_%s' % c] = q_all[offs[ci]:offs[ci + 1]]
+    # End-to-end bar of SURVEY.md section 8(c): 1e-6 -- unless the input noise
+    # forbids it.  The only quantity that is not reproducible to round-off is
+    # disp_per_dist, where the reference itself moves by its summation-order
+    # self-noise (fixture ``disp_selfnoise``: up to 1.2e-6 on these ~450-pixel
+    # bins); a relative change delta of a dispersion moves llr by up to
+    # ~|llr| delta, and p = sf(-2 llr) by a multiple of that.  The tolerance is
+    # therefore max(1e-6, 30 x the MEASURED disp_per_dist difference of this
+    # run), and the measured difference must itself stay within 3x the
+    # reference's self-noise (test_dispersion_per_distance).  At full size
+    # (tests/test_gpu_config1.py, ~11 k-pixel bins) the plain 1e-6 holds.
+    got_dpd = np.load(os.path.join(outdir, 'disp_per_dist.npy'))
+    ref_dpd = gold['g']['disp_per_dist']
+    ok = np.isfinite(ref_dpd)
+    delta = float(np.max(np.abs(got_dpd[ok] - ref_dpd[ok]) / ref_dpd[ok])) \
+        if same_branch else 0.0
+    tol = max(1e-6, 30 * delta)
+    print('end to end: disp_per_dist differs by %.2e, tolerance %.2e'
+          % (delta, tol))
     for c in gold['chroms']:
         ld = lambda n: np.load(os.path.join(outdir, '%s_%s.npy' % (n, c)))
-        np.testing.assert_allclose(ld('disp'), g['disp_%s' % c], rtol=1e-5)
+        np.testing.assert_allclose(ld('disp'), g['disp_%s' % c], rtol=tol)
         np.testing.assert_allclose(ld('mu_hat_null'), g['mu_hat_null_%s' % c],
-                                   rtol=1e-5)
-        np.testing.assert_allclose(ld('llr'), g['llr_%s' % c], rtol=1e-4,
+                                   rtol=tol)
+        np.testing.assert_allclose(ld('llr'), g['llr_%s' % c], rtol=tol,
                                    atol=1e-9)
         q, wq = ld('qvalues'), g['qvalues_%s' % c]
-        np.testing.assert_allclose(q, wq, rtol=1e-4, atol=1e-12)
+        np.testing.assert_allclose(q, wq, rtol=tol, atol=1e-12)
         for fdr in (0.05, 0.2, 0.5):
-            near = np.abs(wq - fdr) <= 1e-4 * fdr
+            near = np.abs(wq - fdr) <= tol * fdr
             assert np.array_equal((q < fdr)[~near], (wq < fdr)[~near])
 
 
@@ -213,11 +232,20 @@ def test_steps_work_from_disk_alone(run):
             np.load(os.path.join(outdir, 'pvalues_%s.npy' % c)), pb[c])
         np.testing.assert_array_equal(
             np.load(os.path.join(outdir, 'qvalues_%s.npy' % c)), before[c])
+    # estimate_disp from the files alone reproduces the table and every disp
+    dpd_before = np.load(os.path.join(outdir, 'disp_per_dist.npy'))
+    disp_before = {c: np.load(os.path.join(outdir, 'disp_%s.npy' % c))
+                   for c in gold['chroms']}
+    os.remove(os.path.join(outdir, 'disp_per_dist.npy'))
+    for c in gold['chroms']:
+        os.remove(os.path.join(outdir, 'disp_%s.npy' % c))
     h3 = HiC3DeFDR.load(outdir)
     h3.estimate_disp(n_threads=0)
     np.testing.assert_array_equal(
-        np.load(os.path.join(outdir, 'disp_per_dist.npy')),
-        np.load(os.path.join(outdir, 'disp_per_dist.npy')))
+        np.load(os.path.join(outdir, 'disp_per_dist.npy')), dpd_before)
+    for c in gold['chroms']:
+        np.testing.assert_array_equal(
+            np.load(os.path.join(outdir, 'disp_%s.npy' % c)), disp_before[c])
 
 
 def test_load_data_semantics(run):

@@ -170,3 +170,53 @@ def test_table_log_and_stirling_core(L):
     scale = np.maximum(np.abs(ref), 25.0)
     # a handful of roundings at that magnitude: under 5 ulp
     assert (np.abs(out - ref) / scale).max() < 1e-15
+
+
+def host_equalize(L, x, f, alpha):
+    """equalize (scaled_nb.py:207-214) from the host build of fit_mu and
+    q2q_one, with the replicate-ordered clamp of equalize_kernel"""
+    n, r = x.shape
+    xs = np.ascontiguousarray(x, dtype=float)
+    fs = np.ascontiguousarray(f, dtype=float)
+    mu = np.zeros(n)
+    st = np.zeros(n, dtype=np.int32)
+    L.hc_fit_mu(P(xs), P(fs), P(np.full((n, r), float(alpha))), n, r, P(mu),
+                st.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
+    assert not st.any()
+    mu_out = mu * np.exp(np.log(fs).sum(axis=1) / r)
+    out = np.zeros((n, r))
+    for k in range(r):
+        mi = mu * fs[:, k]
+        low = ~((mi >= 0.25) & (mu_out >= 0.25))    # scaled_nb.py:240-242:
+        mi[low] = 0.25                              # mu_out is shared by the
+        mu_out[low] = 0.25                          # later replicates
+        col = np.zeros(n)
+        L.hc_q2q(P(xs[:, k].copy()), P(mi), P(mu_out.copy()),
+                 ctypes.c_double(alpha), n, P(col))
+        out[:, k] = col
+    return out
+
+
+def check_pseudo(got, want, rtol=1e-9):
+    """pseudo-data parity: the same entries are infinite (the reference's
+    tail-probability underflow), the finite ones agree to ``rtol`` relative to
+    max(value, 1e-3) -- tiny outputs are differences of the normal and the
+    gamma map that nearly cancel"""
+    assert got.shape == want.shape
+    assert np.array_equal(np.isposinf(got), np.isposinf(want))
+    assert not np.isnan(got).any() and not np.isnan(want).any()
+    m = np.isfinite(want)
+    err = np.abs(got[m] - want[m]) / np.maximum(want[m], 1e-3)
+    assert err.max() < rtol, err.max()
+    return float(err.max())
+
+
+@pytest.mark.parametrize('case', ['small', 'tails', 'grid', 'three'])
+def test_equalize_edges_vs_recorded_reference(L, case):
+    """host build of the device code on the reference's recorded edge cases
+    (tests/golden/make_golden_equalize.py); the device run of the same fixture
+    is tests/test_gpu_disp.py::test_equalize_device_vs_recorded_reference"""
+    g = np.load(os.path.join(HERE, 'golden', 'ref_equalize_edges.npz'))
+    x, f = g['%s_x' % case], g['%s_f' % case]
+    for a in g['alphas']:
+        check_pseudo(host_equalize(L, x, f, a), g['%s_%g' % (case, a)])
