@@ -52,6 +52,8 @@ SIGNATURES = {
     'h3d_equalize': (c_int, [vp, vp, c_ll, c_ll, c_int, c_dbl, vp, vp, vp,
                              c_sz, vp]),
     'h3d_equalize_ws_bytes': (c_sz, [c_ll]),
+    'h3d_cml_nll': (c_int, [vp, c_ll, c_ll, c_int, c_dbl, vp, vp, c_sz, vp]),
+    'h3d_cml_nll_ws_bytes': (c_sz, [c_ll]),
     'h3d_lowess': (c_int, [vp, vp, c_int, c_dbl, c_int, c_dbl, vp, vp, c_sz,
                            vp]),
     'h3d_lowess_ws_bytes': (c_sz, [c_int]),

@@ -5,9 +5,9 @@
 // p-values, sort ascending, q_(i) = p_(i) / (i / n), running minimum from the
 // largest p downwards, clip at 1, undo the sort; non-finite entries stay NaN.
 //
-// HBM-bound.  The sort is an LSD radix sort (6 passes of 11 bits) built on the
-// library's own stable counting-rank primitive (rank.cu); the suffix minimum
-// is a three-phase tiled scan.
+// HBM-bound.  The sort is the one-sweep-per-digit LSD radix sort of sort.cu
+// (8 sweeps of 8 bits, 200 B moved per p-value); the suffix minimum is a
+// three-phase tiled scan.
 #include "common.cuh"
 
 namespace h3d {
@@ -22,7 +22,7 @@ constexpr int kBhTile = 2048;
 constexpr int kKeysPerBlock = 4096;
 __global__ void __launch_bounds__(256)
 bh_keys_kernel(const double* __restrict__ p, long long n, unsigned long long* __restrict__ keys,
-               int* __restrict__ idx, unsigned long long* __restrict__ n_finite) {
+               unsigned long long* __restrict__ n_finite) {
     __shared__ int sh[8];
     const long long base = (long long)blockIdx.x * kKeysPerBlock;
     int cnt = 0;
@@ -35,7 +35,6 @@ bh_keys_kernel(const double* __restrict__ p, long long n, unsigned long long* __
             unsigned long long b = (unsigned long long)__double_as_longlong(v);
             b = (b >> 63) ? ~b : (b | 0x8000000000000000ull);
             keys[i] = fin ? b : kNonFinite;
-            idx[i] = (int)i;
             cnt += fin ? 1 : 0;
         }
     }
@@ -47,25 +46,6 @@ bh_keys_kernel(const double* __restrict__ p, long long n, unsigned long long* __
         int t = 0;
         for (int w = 0; w < 8; ++w) t += sh[w];
         if (t) atomicAdd(n_finite, (unsigned long long)t);
-    }
-}
-
-__global__ void __launch_bounds__(256)
-bh_digit_kernel(const unsigned long long* __restrict__ keys, long long n, int shift, int mask,
-                int* __restrict__ digit) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) digit[i] = (int)((keys[i] >> shift) & (unsigned long long)mask);
-}
-
-__global__ void __launch_bounds__(256)
-bh_scatter_kernel(const unsigned long long* __restrict__ keys_in, const int* __restrict__ idx_in,
-                  const int* __restrict__ rank, long long n, unsigned long long* __restrict__ keys_out,
-                  int* __restrict__ idx_out) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        const int r = rank[i];
-        keys_out[r] = keys_in[i];
-        idx_out[r] = idx_in[i];
     }
 }
 
@@ -200,13 +180,18 @@ bh_apply_carry_kernel(double* __restrict__ q, long long n, double carry) {
 
 using namespace h3d;
 
-static const int kDigitBits[6] = {11, 11, 11, 11, 11, 9};
+namespace h3d {
+// sort.cu
+size_t sort_pairs_ws(long long n);
+int sort_pairs_u64(unsigned long long* keys_a, int* idx_a, unsigned long long* keys_b, int* idx_b,
+                   long long n, void* ws, size_t ws_bytes, cudaStream_t st);
+}
 
 extern "C" size_t h3d_bh_ws_bytes(long long n) {
     if (n < 1) n = 1;
     const long long tiles = (n + kBhTile - 1) / kBhTile;
-    return 2 * ws_pad((size_t)n * 8) + 4 * ws_pad((size_t)n * 4) + stable_rank_ws(n, 2048) +
-           ws_pad(2049 * 8) + 2 * ws_pad((size_t)tiles * 8) + ws_pad(64);
+    return 2 * ws_pad((size_t)n * 8) + 2 * ws_pad((size_t)n * 4) + ws_pad(sort_pairs_ws(n)) +
+           2 * ws_pad((size_t)tiles * 8) + ws_pad(64);
 }
 
 extern "C" int h3d_bh(const double* p, long long n, double* q, void* ws, size_t ws_bytes,
@@ -233,7 +218,7 @@ extern "C" int h3d_bh_ranked(const double* p, long long n, long long rank_offset
         }
         return H3D_OK;
     }
-    H3D_REQUIRE(n < 2147483647LL, "more than 2^31 p-values");
+    H3D_REQUIRE(n < (1LL << 30), "more than 2^30 p-values on one device");
     H3D_REQUIRE(rank_offset >= 0 && n_total >= 0, "negative rank offset / total");
     const BhScope sc = {rank_offset, n_total};
     Workspace w(ws, ws_bytes);
@@ -242,39 +227,20 @@ extern "C" int h3d_bh_ranked(const double* p, long long n, long long rank_offset
     unsigned long long* keys_b = w.take<unsigned long long>(n);
     int* idx_a = w.take<int>(n);
     int* idx_b = w.take<int>(n);
-    int* digit = w.take<int>(n);
-    int* rank = w.take<int>(n);
-    const size_t rws = stable_rank_ws(n, 2048);
-    void* rank_ws = w.take<char>(rws);
-    long long* key_start = w.take<long long>(2049);
+    const size_t sws = sort_pairs_ws(n);
+    void* sort_ws = w.take<char>(sws);
     double* tile_min = w.take<double>(tiles);
     double* carry = w.take<double>(tiles);
     unsigned long long* n_finite = w.take<unsigned long long>(1);
-    if (!keys_a || !keys_b || !idx_a || !idx_b || !digit || !rank || !rank_ws || !key_start ||
-        !tile_min || !carry || !n_finite) {
+    if (!keys_a || !keys_b || !idx_a || !idx_b || !sort_ws || !tile_min || !carry || !n_finite) {
         set_error("bh workspace too small");
         return H3D_ERR_WORKSPACE;
     }
-    const int grid = div_up(n, 256);
     H3D_CHECK(cudaMemsetAsync(n_finite, 0, 8, st));
-    bh_keys_kernel<<<div_up(n, kKeysPerBlock), 256, 0, st>>>(p, n, keys_a, idx_a, n_finite);
+    bh_keys_kernel<<<div_up(n, kKeysPerBlock), 256, 0, st>>>(p, n, keys_a, n_finite);
     H3D_LAUNCHED("bh_keys_kernel");
-    int shift = 0;
-    for (int pass = 0; pass < 6; ++pass) {
-        const int bits = kDigitBits[pass];
-        // digit array + rank + separate scatter: measured faster on B200 than taking the
-        // digit from the 64-bit key inside the rank kernels and moving the pair from the
-        // (latency-bound, warp-serial) emit pass (radix_pass_u64: 16.1 vs 11.5 ms for 38.7 M)
-        bh_digit_kernel<<<grid, 256, 0, st>>>(keys_a, n, shift, (1 << bits) - 1, digit);
-        H3D_LAUNCHED("bh_digit_kernel");
-        int rc = stable_rank_impl(digit, n, 1 << bits, rank, key_start, rank_ws, rws, st);
-        if (rc) return rc;
-        bh_scatter_kernel<<<grid, 256, 0, st>>>(keys_a, idx_a, rank, n, keys_b, idx_b);
-        H3D_LAUNCHED("bh_scatter_kernel");
-        unsigned long long* tk = keys_a; keys_a = keys_b; keys_b = tk;
-        int* ti = idx_a; idx_a = idx_b; idx_b = ti;
-        shift += bits;
-    }
+    // ascending by p, payload = original position; non-finite keys sort last
+    { int rc = sort_pairs_u64(keys_a, idx_a, keys_b, idx_b, n, sort_ws, sws, st); if (rc) return rc; }
     bh_tile_min_kernel<<<(int)tiles, 256, 0, st>>>(keys_a, n_finite, sc, tile_min);
     H3D_LAUNCHED("bh_tile_min_kernel");
     bh_tile_scan_kernel<<<1, 1024, 0, st>>>(tile_min, n_finite, carry, min_out);

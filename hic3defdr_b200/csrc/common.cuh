@@ -87,11 +87,6 @@ __device__ __forceinline__ double load_value(const void* p, long long i, int dty
 int stable_rank_impl(const int* keys, long long n, int n_keys, int* rank_out,
                      long long* key_start, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t stable_rank_ws(long long n, int n_keys);
-// rank.cu: one stable LSD radix pass over (64-bit key, int payload) pairs
-int radix_pass_u64(const unsigned long long* keys_in, const int* idx_in, long long n, int shift,
-                   int bits, unsigned long long* keys_out, int* idx_out, long long* key_start,
-                   void* ws, size_t ws_bytes, cudaStream_t st);
-
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);

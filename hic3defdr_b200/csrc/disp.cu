@@ -87,24 +87,28 @@ __global__ void init_problems_kernel(Problem* __restrict__ prob, const long long
 #ifndef H3D_EQ_TASKS
 #define H3D_EQ_TASKS 512
 #endif
-constexpr int kEqTasks = H3D_EQ_TASKS;      // task slots per batch (28 B of shared memory each)
+constexpr int kEqTasks = H3D_EQ_TASKS;      // task slots per batch (32 B of shared memory each)
 
 struct EqTask { double x, mu_in, mu_out; };
 
-// Task order inside a batch.  0: two lists (continued-fraction tasks from the
-// front, series tasks from the back).  N > 0: each of the two lists is further
-// ordered by the predicted trip count of its incomplete-gamma loop, in N cost
-// buckets of a quarter octave each (counting sort through shared-memory
-// counters), so that the 32 tasks a warp runs together have similar lengths
-// (A/B on B200, mouse genome: 84.9 -> 81.5 ms per step; 2 or 6 buckets per octave
-// are within 1 %, 8 are slower).  Also measured and rejected: splitting the
-// quantile map after the first evaluation of its inverse and running the ~40 %
-// of the tasks that need another one as a compacted second pass -- the resumable
-// form of the Halley loop costs more (spills) than the idle lanes it saves.
+// Task order inside a batch: continued-fraction tasks first, series tasks
+// after them, and inside each of the two lists by the predicted trip count of
+// the incomplete-gamma loop, in cost buckets of a quarter octave each (counting
+// sort through shared-memory counters), so that the 32 tasks a warp runs
+// together take the same branch and have similar lengths (A/B on B200, mouse
+// genome: 84.9 -> 81.5 ms per step; 2 or 6 buckets per octave are within 1 %,
+// 8 are slower).  Warps then take groups of 32 consecutive tasks from the
+// expensive end of the order through a shared counter, so that no warp waits
+// at the batch's closing barrier for longer than one cheap group (barrier
+// stalls were 13.6 % of the warp samples with a static assignment, ncu r01g).
+// Also measured and rejected: splitting the quantile map after the first
+// evaluation of its inverse and running the ~40 % of the tasks that need
+// another one as a compacted second pass -- the resumable form of the Halley
+// loop costs more (spills) than the idle lanes it saves.
 #ifndef H3D_EQ_BUCKETS
 #define H3D_EQ_BUCKETS 48
 #endif
-constexpr int kEqNB = H3D_EQ_BUCKETS > 0 ? H3D_EQ_BUCKETS : 1;
+constexpr int kEqNB = H3D_EQ_BUCKETS;
 #ifndef H3D_EQ_BUCKET_SCALE
 #define H3D_EQ_BUCKET_SCALE 4.0f            // buckets per octave of predicted trip count
 #endif
@@ -136,13 +140,12 @@ equalize_kernel(const double* __restrict__ x, const double* __restrict__ f, long
                 const long long* __restrict__ seg_start, CondReps cr, int estimator,
                 const Problem* __restrict__ prob, double* __restrict__ pseudo, Counters* cnt) {
     extern __shared__ unsigned char eq_smem[];
-    EqTask* task = (EqTask*)eq_smem;
-    int* task_dest = (int*)(eq_smem + (size_t)kEqTasks * sizeof(EqTask));
-    __shared__ int n_right, n_left;
-#if H3D_EQ_BUCKETS
+    EqTask* task = (EqTask*)eq_smem;                                    // [slot]
+    int* task_code = (int*)(eq_smem + (size_t)kEqTasks * sizeof(EqTask));   // [slot]: (list << 16) | position, -1: none
+    int* order = task_code + kEqTasks;                                  // [position in processing order] -> slot
     __shared__ int bucket_cnt[2 * kEqNB];       // [continued fraction | series] x cost bucket
     __shared__ int bucket_base[2 * kEqNB + 1];
-#endif
+    __shared__ int next_group;
     const int c = blockIdx.y;
     const int s = chunk_seg[blockIdx.x];
     const Problem& q = prob[s * cr.n_conds + c];
@@ -153,20 +156,25 @@ equalize_kernel(const double* __restrict__ x, const double* __restrict__ f, long
     const long long hi = (lo + kChunk < seg_hi) ? lo + kChunk : seg_hi;
     const int nr = cr.n_in[c];
     const int lane = threadIdx.x & 31;
-    const unsigned lt_mask = (1u << lane) - 1u;
     double* __restrict__ out_base = pseudo + (long long)cr.pseudo_row[c] * ld;
     constexpr int kBatchPx = kEqTasks / MAXRC;
-    static_assert(H3D_EQ_BUCKETS == 0 || kBatchPx <= 256, "one pixel per thread and batch");
-    for (long long b0 = lo; b0 < hi; b0 += kBatchPx) {
-        if (threadIdx.x == 0) { n_right = 0; n_left = 0; }
-#if H3D_EQ_BUCKETS
-        for (int b = threadIdx.x; b < 2 * kEqNB; b += 256) bucket_cnt[b] = 0;
-        int code[MAXRC];                        // (list << 16) | position inside the list, -1: no task
+    if (estimator == H3D_EST_CML) {
+        // cml(raw, f): data / f (dispersion.py:67-68, intended semantics)
+        for (long long i = lo + threadIdx.x; i < hi; i += 256)
 #pragma unroll
-        for (int k = 0; k < MAXRC; ++k) code[k] = -1;
-#endif
+            for (int k = 0; k < MAXRC; ++k)
+                if (k < nr) {
+                    const int r = cr.rep[c][k];
+                    out_base[(long long)k * ld + i] = x[(long long)r * ld + i] / f[(long long)r * ld + i];
+                }
+        return;
+    }
+    for (long long b0 = lo; b0 < hi; b0 += kBatchPx) {
+        for (int b = threadIdx.x; b < 2 * kEqNB; b += 256) bucket_cnt[b] = 0;
+        if (threadIdx.x == 0) next_group = 0;
         __syncthreads();
         const long long b1 = (b0 + kBatchPx < hi) ? b0 + kBatchPx : hi;
+        // ---- per pixel: fit_mu, clamped means, task records -------------
         for (long long i0 = b0; i0 < b1; i0 += 256) {
             const long long i = i0 + threadIdx.x;
             const bool valid = i < b1;
@@ -181,13 +189,6 @@ equalize_kernel(const double* __restrict__ x, const double* __restrict__ f, long
                     fr[k] = f[(long long)r * ld + i];
                     slog += m_log(fr[k]);
                 }
-            }
-            if (estimator == H3D_EST_CML) {
-                // cml(raw, f): data / f (dispersion.py:67-68, intended semantics)
-#pragma unroll
-                for (int k = 0; k < MAXRC; ++k)
-                    if (valid && k < nr) out_base[(long long)k * ld + i] = xr[k] / fr[k];
-                continue;
             }
             // equalize (scaled_nb.py:207-214)
             double mu_hat = 1.0, mu_out = 1.0;
@@ -208,50 +209,27 @@ equalize_kernel(const double* __restrict__ x, const double* __restrict__ f, long
                     const bool cheap = !right && !(xr[k] > 0.0);     // no gamma evaluation needed
                     if (valid && cheap)
                         out_base[(long long)k * ld + i] = q2q_zero(mu_in, mu_out, alpha);
-                    const bool push = valid && !cheap;
-                    // which algorithm the tail evaluations of this task will use
-                    // (FP32 copy of gamma_use_series: only a scheduling hint)
-                    const float rin_f = 1.0f + (float)alpha * (float)mu_in;
-                    const bool front = !gamma_use_series((double)((float)mu_in / rin_f),
-                                                         (double)((float)xr[k] / rin_f));
-#if H3D_EQ_BUCKETS
-                    if (push) {
-                        // the slot is the task's own (replicate, pixel) position; its
-                        // place in the processing order is settled after the batch's
-                        // counters are complete
-                        const int list = (front ? 0 : kEqNB) +
-                                         eq_cost_bucket((float)mu_in / rin_f, (float)xr[k] / rin_f, !front);
-                        code[k] = (list << 16) | atomicAdd(&bucket_cnt[list], 1);
-                        const int slot = k * kBatchPx + (int)(i - b0);
+                    const int slot = k * kBatchPx + (int)(i - b0);
+                    int code = -1;
+                    if (valid && !cheap) {
+                        // which algorithm the tail evaluations of this task will use
+                        // (FP32 copy of gamma_use_series: only a scheduling hint)
+                        const float rin_f = 1.0f + (float)alpha * (float)mu_in;
+                        const float a_f = (float)mu_in / rin_f, x_f = (float)xr[k] / rin_f;
+                        const bool series = gamma_use_series((double)a_f, (double)x_f);
+                        const int list = (series ? kEqNB : 0) + eq_cost_bucket(a_f, x_f, series);
+                        // the task stays in its own (replicate, pixel) slot; its place in
+                        // the processing order is settled once the batch's counters are complete
+                        code = (list << 16) | atomicAdd(&bucket_cnt[list], 1);
                         task[slot].x = xr[k];
                         task[slot].mu_in = mu_in;
                         task[slot].mu_out = mu_out;
                     }
-                    continue;
-#endif
-                    const unsigned m_r = __ballot_sync(0xffffffffu, push && front);
-                    const unsigned m_l = __ballot_sync(0xffffffffu, push && !front);
-                    int base_r = 0, base_l = 0;
-                    if (lane == 0) {
-                        if (m_r) base_r = atomicAdd(&n_right, __popc(m_r));
-                        if (m_l) base_l = atomicAdd(&n_left, __popc(m_l));
-                    }
-                    base_r = __shfl_sync(0xffffffffu, base_r, 0);
-                    base_l = __shfl_sync(0xffffffffu, base_l, 0);
-                    if (push) {
-                        const int slot = front ? base_r + __popc(m_r & lt_mask)
-                                               : kEqTasks - 1 - (base_l + __popc(m_l & lt_mask));
-                        task[slot].x = xr[k];
-                        task[slot].mu_in = mu_in;
-                        task[slot].mu_out = mu_out;
-                        task_dest[slot] = k * kBatchPx + (int)(i - b0);
-                    }
+                    if (i - b0 < kBatchPx) task_code[slot] = code;
                 }
             }
         }
         __syncthreads();
-        if (estimator == H3D_EST_CML) continue;
-#if H3D_EQ_BUCKETS
         if (threadIdx.x < 32) {
             // exclusive scan of the 2 * kEqNB counters by warp 0: each lane owns a
             // contiguous run of them
@@ -280,39 +258,33 @@ equalize_kernel(const double* __restrict__ x, const double* __restrict__ f, long
             if (threadIdx.x == 31) bucket_base[2 * kEqNB] = incl;
         }
         __syncthreads();
-#pragma unroll
-        for (int k = 0; k < MAXRC; ++k)
-            if (code[k] >= 0)
-                task_dest[bucket_base[code[k] >> 16] + (code[k] & 0xffff)] =
-                    k * kBatchPx + (int)threadIdx.x;
+        {
+            const int n_px = (int)(b1 - b0);
+            for (int k = 0; k < nr; ++k)
+                for (int j = threadIdx.x; j < n_px; j += 256) {
+                    const int slot = k * kBatchPx + j;
+                    const int code = task_code[slot];
+                    if (code >= 0) order[bucket_base[code >> 16] + (code & 0xffff)] = slot;
+                }
+        }
         __syncthreads();
         {
+            // groups of 32 consecutive tasks, from the expensive end of the order
             const int n_tasks = bucket_base[2 * kEqNB];
-            for (int t0 = 0; t0 < n_tasks; t0 += 256) {
-                const int t = t0 + threadIdx.x;
+            const int n_groups = (n_tasks + 31) >> 5;
+            while (true) {
+                int g = 0;
+                if (lane == 0) g = atomicAdd(&next_group, 1);
+                g = __shfl_sync(0xffffffffu, g, 0);
+                if (g >= n_groups) break;
+                const int t = ((n_groups - 1 - g) << 5) + lane;
                 if (t < n_tasks) {
-                    const int slot = task_dest[t];
+                    const int slot = order[t];
                     const EqTask tk = task[slot];
                     const int k = slot / kBatchPx;
                     const long long i = b0 + (slot - k * kBatchPx);
                     out_base[(long long)k * ld + i] = q2q_one(tk.x, tk.mu_in, tk.mu_out, alpha);
                 }
-            }
-        }
-        __syncthreads();
-        continue;
-#endif
-        const int nR = n_right, nL = n_left;
-        // continued-fraction tasks [0, nR), then series tasks [kEqTasks - nL, kEqTasks)
-        for (int t0 = 0; t0 < nR + nL; t0 += 256) {
-            const int t = t0 + threadIdx.x;
-            if (t < nR + nL) {
-                const int slot = (t < nR) ? t : kEqTasks - 1 - (t - nR);
-                const EqTask tk = task[slot];
-                const int dst = task_dest[slot];
-                const int k = dst / kBatchPx;
-                const long long i = b0 + (dst - k * kBatchPx);
-                out_base[(long long)k * ld + i] = q2q_one(tk.x, tk.mu_in, tk.mu_out, alpha);
             }
         }
         __syncthreads();
@@ -587,12 +559,18 @@ __global__ void collect_kernel(const Problem* __restrict__ prob, int n, double* 
 // one problem per condition over a single segment, waiting for pseudo-data at a
 // given dispersion (h3d_equalize)
 __global__ void single_bin_problems_kernel(Problem* prob, int n_conds, long long n_px, double alpha,
-                                           Counters* cnt) {
+                                           double delta, int status, Counters* cnt) {
     const int p = threadIdx.x;
     if (p == 0) { cnt->n_need_eq = 0; cnt->n_in_brent = 0; cnt->n_failed = 0; cnt->n_fit_failed = 0; }
     if (p >= n_conds) return;
     prob[p].n_px = n_px; prob[p].outer_iters = 0; prob[p].nfev_total = 0;
-    prob[p].disp = alpha; prob[p].status = ST_NEED_EQ;
+    prob[p].disp = alpha; prob[p].status = status;
+    brent_begin(prob[p].brent, kDeltaLo, kDeltaHi);
+    prob[p].brent.x_eval = delta;
+}
+
+__global__ void fix_value_kernel(const Fix128* acc, double* out) {
+    out[0] = acc->bad ? NAN : -fix_value(*acc);
 }
 
 }  // namespace h3d
@@ -771,7 +749,7 @@ extern "C" int h3d_estimate_dispersion(const double* x, const double* f, long lo
     volatile RoundSlot* ring_host = (volatile RoundSlot*)pin_host;
     RoundSlot* ring_dev = (RoundSlot*)pin_dev;
     for (int k = 0; k < ring; ++k) ring_host[k].seq = 0;     // nothing of an earlier call is in flight
-    const size_t eq_smem = (size_t)kEqTasks * (sizeof(EqTask) + sizeof(int));
+    const size_t eq_smem = (size_t)kEqTasks * (sizeof(EqTask) + 2 * sizeof(int));
     { int rc = set_equalize_smem(eq_smem); if (rc) return rc; }
     // per-kernel device time of the two heavy kernels (CUDA events on the
     // launching stream, read once the round's counters have arrived)
@@ -919,9 +897,9 @@ extern "C" int h3d_equalize(const double* x, const double* f, long long ld, long
     Problem* prob = w.take<Problem>(1);
     Counters* cnt = w.take<Counters>(1);
     if (!prob || !cnt) { set_error("equalize workspace too small (%zu bytes given)", ws_bytes); return H3D_ERR_WORKSPACE; }
-    single_bin_problems_kernel<<<1, 32, 0, st>>>(prob, 1, n_px, alpha, cnt);
+    single_bin_problems_kernel<<<1, 32, 0, st>>>(prob, 1, n_px, alpha, 0.5, ST_NEED_EQ, cnt);
     H3D_LAUNCHED("single_bin_problems_kernel");
-    const size_t eq_smem = (size_t)kEqTasks * (sizeof(EqTask) + sizeof(int));
+    const size_t eq_smem = (size_t)kEqTasks * (sizeof(EqTask) + 2 * sizeof(int));
     { int rc = set_equalize_smem(eq_smem); if (rc) return rc; }
     const dim3 cgrid(ct.n_chunks, 1);
 #define CALL(M) equalize_kernel<M><<<cgrid, 256, eq_smem, st>>>(x, f, ld, ct.chunk_seg, ct.chunk_lo, ct.seg_start, cr, \
@@ -931,5 +909,44 @@ extern "C" int h3d_equalize(const double* x, const double* f, long long ld, long
     H3D_LAUNCHED("equalize_kernel");
     if (n_fit_failed)
         H3D_CHECK(cudaMemcpyAsync(n_fit_failed, &cnt->n_fit_failed, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    return H3D_OK;
+}
+
+// Conditional NB negative log-likelihood of ONE bin of (pseudo-)data at
+// delta = disp / (1 + disp): the objective of hic3defdr/util/dispersion.py:
+// 72-75, evaluated by the kernel the qCML driver launches (exact 128-bit sum).
+// data: SoA (n_reps, ld); nll_out: one double on the device.
+extern "C" size_t h3d_cml_nll_ws_bytes(long long n_px) {
+    return h3d_equalize_ws_bytes(n_px) + ws_pad(sizeof(Fix128));
+}
+
+extern "C" int h3d_cml_nll(const double* data, long long ld, long long n_px, int n_reps, double delta,
+                           double* nll_out, void* ws, size_t ws_bytes, h3d_stream_t stream) {
+    H3D_REQUIRE(n_reps >= 1 && n_reps <= H3D_MAX_REPS, "n_reps out of range");
+    H3D_REQUIRE(n_px >= 1 && n_px <= ld, "n_px must be in [1, ld]");
+    H3D_REQUIRE(delta > 0.0 && delta < 1.0, "delta must be in (0, 1)");
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<unsigned char> design(n_reps, 1);
+    CondReps cr;
+    int rows = 0, max_rc = 0;
+    { int rc = make_cond_reps(design.data(), n_reps, 1, &cr, &rows, &max_rc); if (rc) return rc; }
+    const long long seg[2] = {0, n_px};
+    Workspace w(ws, ws_bytes);
+    ChunkTables ct;
+    { int rc = make_chunk_tables(seg, 1, w, st, &ct); if (rc) return rc; }
+    Problem* prob = w.take<Problem>(1);
+    Counters* cnt = w.take<Counters>(1);
+    Fix128* acc = w.take<Fix128>(1);
+    if (!prob || !cnt || !acc) { set_error("cml_nll workspace too small (%zu bytes given)", ws_bytes); return H3D_ERR_WORKSPACE; }
+    H3D_CHECK(cudaMemsetAsync(acc, 0, sizeof(Fix128), st));
+    single_bin_problems_kernel<<<1, 32, 0, st>>>(prob, 1, n_px, 0.0, delta, ST_IN_BRENT, cnt);
+    H3D_LAUNCHED("single_bin_problems_kernel");
+    const dim3 cgrid(ct.n_chunks, 1);
+#define CALL(M) nll_kernel<M><<<cgrid, 256, 0, st>>>(data, ld, ct.chunk_seg, ct.chunk_lo, ct.seg_start, cr, prob, acc)
+    DISPATCH_RC(CALL)
+#undef CALL
+    H3D_LAUNCHED("nll_kernel");
+    fix_value_kernel<<<1, 1, 0, st>>>(acc, nll_out);
+    H3D_LAUNCHED("fix_value_kernel");
     return H3D_OK;
 }

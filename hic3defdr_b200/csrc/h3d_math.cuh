@@ -26,11 +26,16 @@
 
 // optional host-side instrumentation (tests/hostcheck only)
 #ifdef H3D_HOST_STATS
-struct H3dStats { long long n_tail_eval, n_series_it, n_cf_it, n_q2q; };
+struct H3dStats { long long n_tail_eval, n_series_it, n_cf_it, n_q2q; long long step_hist[16]; long long evals_hist[8]; };
 extern H3dStats g_h3d_stats;
 #define H3D_STAT(field) (++g_h3d_stats.field)
+#define H3D_STAT_STEP(it, rel) do { if ((it) == 0) { int b_ = (int)(-log10((rel) + 1e-300)); \
+    ++g_h3d_stats.step_hist[b_ < 0 ? 0 : (b_ > 15 ? 15 : b_)]; } } while (0)
+#define H3D_STAT_EVALS(n) (++g_h3d_stats.evals_hist[(n) > 7 ? 7 : (n)])
 #else
 #define H3D_STAT(field) ((void)0)
+#define H3D_STAT_STEP(it, rel) ((void)0)
+#define H3D_STAT_EVALS(n) ((void)0)
 #endif
 
 // Halley iteration of the incomplete-gamma inverse: a step smaller than this
@@ -81,6 +86,13 @@ static __constant__ double kDevLogPoly[6] = {1.0 / 7.0, -1.0 / 6.0, 1.0 / 5.0, -
 static __constant__ double kDevStirling[7] = {1.0 / 12.0, -1.0 / 360.0, 1.0 / 1260.0, -1.0 / 1680.0,
                                               1.0 / 1188.0, -691.0 / 360360.0, 1.0 / 156.0};
 static __constant__ double kDevLn2[2] = {0.693147180559945286, 2.319046813846299616e-17};
+// 1/27, 1/25, ..., 1/3: the atanh series of log1p_minus_x
+static __constant__ double kDevAtanh[13] = {1.0 / 27.0, 1.0 / 25.0, 1.0 / 23.0, 1.0 / 21.0, 1.0 / 19.0,
+                                            1.0 / 17.0, 1.0 / 15.0, 1.0 / 13.0, 1.0 / 11.0, 1.0 / 9.0,
+                                            1.0 / 7.0, 1.0 / 5.0, 1.0 / 3.0};
+// 1/10!, 1/9!, ..., 1/2!: exp(u) - 1 - u for small u
+static __constant__ double kDevExpSmall[9] = {1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0, 1.0 / 5040.0,
+                                              1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5};
 // the table itself: 2 KB, read through L1 (a divergent index would serialise
 // in the constant cache)
 static __device__ const LogTabEntry kDevLogTab[kLogTabSize] = {
@@ -242,15 +254,58 @@ H3D_HD double fit_mu(const double* x, const double* b, const double* alpha,
 // continued fraction is evaluated by the forward (Wallis) recurrence of its
 // convergents and only divides when it tests convergence.
 // ---------------------------------------------------------------------------
+// Stirling's correction sum 1/(12x) - 1/(360x^3) + ... given ix = 1/x (x >= 10:
+// truncation < 2e-17).  Device: coefficients as constant-bank operands.
+H3D_HD double stirling_sum(double ix) {
+    const double ix2 = ix * ix;
+#ifdef __CUDA_ARCH__
+    double c = fma(ix2, kDevStirling[6], kDevStirling[5]);
+    c = fma(ix2, c, kDevStirling[4]);
+    c = fma(ix2, c, kDevStirling[3]);
+    c = fma(ix2, c, kDevStirling[2]);
+    c = fma(ix2, c, kDevStirling[1]);
+    c = fma(ix2, c, kDevStirling[0]);
+    return ix * c;
+#else
+    return ix * (1.0 / 12.0 + ix2 * (-1.0 / 360.0 + ix2 * (1.0 / 1260.0 +
+        ix2 * (-1.0 / 1680.0 + ix2 * (1.0 / 1188.0 + ix2 * (-691.0 / 360360.0 +
+        ix2 * (1.0 / 156.0)))))));
+#endif
+}
+
+// exp(u) for the small arguments of a converging iteration (|u| < 1/16: the
+// degree-10 Taylor polynomial is exact to 2e-21), the library routine otherwise
+H3D_HD double exp_step(double u) {
+    if (fabs(u) < 0.0625) {
+#ifdef __CUDA_ARCH__
+        double p = kDevExpSmall[0];
+#pragma unroll
+        for (int k = 1; k < 9; ++k) p = fma(p, u, kDevExpSmall[k]);
+#else
+        const double cf[9] = {1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0, 1.0 / 5040.0,
+                              1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5};
+        double p = cf[0];
+        for (int k = 1; k < 9; ++k) p = fma(p, u, cf[k]);
+#endif
+        return fma(u * u, p, u) + 1.0;
+    }
+    return m_exp(u);
+}
+
 H3D_HD double log1p_minus_x(double u) {
     if (fabs(u) < 0.25) {
         // ln(1+u) - u via the atanh series in w = u / (2 + u):
         // ln(1+u) = 2 (w + w^3/3 + w^5/5 + ...), and 2w - u = -u w
         const double w = u / (2.0 + u);
         const double w2 = w * w;
-        double s = 0.0;
+#ifdef __CUDA_ARCH__
+        double s = kDevAtanh[0];
 #pragma unroll
+        for (int k = 1; k < 13; ++k) s = fma(s, w2, kDevAtanh[k]);
+#else
+        double s = 0.0;
         for (int k = 27; k >= 3; k -= 2) s = s * w2 + 1.0 / (double)k;
+#endif
         return 2.0 * w * w2 * s - u * w;
     }
     return m_log1p(u) - u;
@@ -260,7 +315,6 @@ struct GammaShape {
     double a;
     double lead;   // a >= 10: 0.5 ln(a / 2 pi) - stirling(a);  else: -lgamma(a)
     double inv_a;
-    double lg_a1;  // ln Gamma(a + 1)
     bool big;
 };
 
@@ -271,20 +325,12 @@ H3D_HDN GammaShape gamma_shape(double a) {
     s.a = a;
     s.inv_a = 1.0 / a;
     s.big = a >= 10.0;
-    const double la = m_log(a);
     if (s.big) {
         // direct a ln x - x - lgamma(a) cancels catastrophically for large a;
         // Stirling: ln Gamma(a) = (a - .5) ln a - a + .5 ln 2pi + corr(a)
-        const double ia = s.inv_a, ia2 = ia * ia;
-        const double corr = ia * (1.0 / 12.0 + ia2 * (-1.0 / 360.0 + ia2 * (1.0 / 1260.0 +
-            ia2 * (-1.0 / 1680.0 + ia2 * (1.0 / 1188.0 + ia2 * (-691.0 / 360360.0 +
-            ia2 * (1.0 / 156.0)))))));
-        s.lead = 0.5 * (la - 1.8378770664093453) - corr;
-        s.lg_a1 = (a + 0.5) * la - a + 0.9189385332046727 + corr;
+        s.lead = 0.5 * (m_log(a) - 1.8378770664093453) - stirling_sum(s.inv_a);
     } else {
-        const double lga = lgamma_pos(a);
-        s.lead = -lga;
-        s.lg_a1 = lga + la;
+        s.lead = -lgamma_pos(a);
     }
     return s;
 }
@@ -376,12 +422,17 @@ H3D_HDN void gamma_log_tail(const GammaShape& s, double y, bool upper, double* l
     *log_k = lk;
     const bool series = gamma_use_series(s.a, y);
     const double F = series ? gamma_series_factor(s.a, y) : gamma_cf_factor(s.a, y);
-    const double l_direct = lk + m_log(F);          // log P (series) or log Q (fraction)
-    if (series != upper) { *log_t = l_direct; *ratio = F; return; }
-    // the complementary tail was asked for
-    const double c = m_exp(l_direct);
+    if (series != upper) {
+        *log_t = lk + m_log(F);                     // log P (series) or log Q (fraction)
+        *ratio = F;
+        return;
+    }
+    // the complementary tail was asked for: T = 1 - k F, ratio = T / k
+    // (one exponential; no logarithm of F is needed on this branch)
+    const double k = m_exp(lk);
+    const double c = k * F;
     *log_t = m_log1p(-c);
-    *ratio = (1.0 - c) * m_exp(-lk);
+    *ratio = (1.0 - c) / k;
 }
 
 H3D_HD double gamma_p(double a, double x, double lga) {
@@ -419,9 +470,11 @@ H3D_HD double gamma_log_tail_inv(const GammaShape& s, double lt, bool upper, dou
     const double step_tol = (a > 1.0) ? H3D_HALLEY_TOL / sqrt(a) : H3D_HALLEY_TOL;
     double y = (guess > 0.0 && isfinite(guess)) ? guess : a;
     if (!upper) {
-        // far lower tail: P(a,y) ~ y^a / Gamma(a+1)
-        const double ys = m_exp((lt + s.lg_a1) * s.inv_a);
-        if (ys < 0.2 * (a + 1.0)) y = ys;
+        // far lower tail: P(a,y) ~ y^a / Gamma(a+1).  Only a seed: single
+        // precision (the exponent is bounded: lt > -745, a > 0)
+        const float af = (float)a;
+        const float ys = expf(((float)lt + lgammaf(af + 1.0f)) / af);
+        if (ys < 0.2f * (af + 1.0f) && ys > 0.0f) y = (double)ys;
     }
     if (!(y > 0.0)) y = 1.0;
     for (int it = 0; it < 100; ++it) {
@@ -447,11 +500,12 @@ H3D_HD double gamma_log_tail_inv(const GammaShape& s, double lt, bool upper, dou
                 const double kap = 1.0 / ratio;
                 double den = 2.0 * kap - g * (a - y - kap);
                 if (!(den > kap)) den = 2.0 * kap;
-                nxt = y * m_exp(-2.0 * g / den);
+                nxt = y * exp_step(-2.0 * g / den);
             }
             // a step this small means nxt is converged to round-off (the next
             // correction would be below 1e-18 relative)
-            if (fabs(nxt - y) <= step_tol * fabs(nxt)) return nxt;
+            H3D_STAT_STEP(it, fabs(nxt - y) / fabs(nxt) * (a > 1.0 ? sqrt(a) : 1.0));
+            if (fabs(nxt - y) <= step_tol * fabs(nxt)) { H3D_STAT_EVALS(it + 1); return nxt; }
         }
         if (!((nxt > lo) && (nxt < hi))) {
             // Newton left the bracket (or was not available): bisect
@@ -475,12 +529,12 @@ H3D_HD double gamma_tail_inv(double a, double t, double lga, bool upper, double 
 }
 
 // Wilson-Hilferty: Gamma(a,1) variate as a cube of a normal one.
-H3D_HD double wh_to_normal(double a, double x) {
-    // cube root through the shared log / exp (only seeds an iteration)
-    return (m_exp(m_log(x / a) * (1.0 / 3.0)) - (1.0 - 1.0 / (9.0 * a))) * 3.0 * sqrt(a);
+// (only seeds an iteration: single precision)
+H3D_HD float wh_to_normal(float a, float x) {
+    return (cbrtf(x / a) - (1.0f - 1.0f / (9.0f * a))) * 3.0f * sqrtf(a);
 }
-H3D_HD double wh_from_normal(double a, double z) {
-    const double t = 1.0 - 1.0 / (9.0 * a) + z / (3.0 * sqrt(a));
+H3D_HD float wh_from_normal(float a, float z) {
+    const float t = 1.0f - 1.0f / (9.0f * a) + z / (3.0f * sqrtf(a));
     return a * t * t * t;
 }
 
@@ -541,8 +595,8 @@ H3D_HD double q2q_one(double x, double mu_in, double mu_out, double alpha) {
         } else {
             double guess = xs * (a_out / a_in);
             if (a_in > 2.0 && a_out > 2.0) {
-                const double g2 = wh_from_normal(a_out, wh_to_normal(a_in, xs));
-                if (g2 > 0.0 && isfinite(g2)) guess = g2;
+                const float g2 = wh_from_normal((float)a_out, wh_to_normal((float)a_in, (float)xs));
+                if (g2 > 0.0f && isfinite(g2)) guess = (double)g2;
             }
             q_gamma = r_out * gamma_log_tail_inv(gamma_shape(a_out), lt, right, guess);
         }
@@ -617,10 +671,7 @@ H3D_HD double lgamma_pos(double x) {
         }
         shift = m_log(p);
     }
-    const double ix = 1.0 / x, ix2 = ix * ix;
-    const double corr = ix * (1.0 / 12.0 + ix2 * (-1.0 / 360.0 + ix2 * (1.0 / 1260.0 +
-        ix2 * (-1.0 / 1680.0 + ix2 * (1.0 / 1188.0 + ix2 * (-691.0 / 360360.0 +
-        ix2 * (1.0 / 156.0)))))));
+    const double corr = stirling_sum(1.0 / x);
     return ((x - 0.5) * m_log(x) - x + 0.9189385332046727 + corr) - shift;
 }
 

@@ -55,20 +55,11 @@ static RankPlan make_rank_plan(long long n, int n_keys) {
     return p;
 }
 
-// where a key comes from: an int32 array, or one digit of a 64-bit sort key
-// (the LSD radix passes of bh.cu: no separate digit array, no separate scatter)
+// where a key comes from
 struct IntKeys {
     const int* __restrict__ keys;
     __device__ __forceinline__ int operator()(long long i) const { return keys[i]; }
 };
-struct DigitKeys {
-    const unsigned long long* __restrict__ keys;
-    int shift, mask;
-    __device__ __forceinline__ int operator()(long long i) const {
-        return (int)((keys[i] >> shift) & (unsigned long long)mask);
-    }
-};
-
 template <typename KeyFn>
 __global__ void rank_hist_kernel(KeyFn keys, long long n, int n_keys,
                                  int seg_len, int n_segs, int* __restrict__ table,
@@ -186,23 +177,11 @@ key_start_kernel(const long long* __restrict__ key_total, int n_keys, long long*
     if (threadIdx.x == 0) key_start[n_keys] = carry;
 }
 
-// what happens with an element's position: stored (stable_rank), or used at
-// once to move the (sort key, payload) pair there (radix pass)
+// what happens with an element's position
 struct StoreRank {
     int* __restrict__ rank_out;
     __device__ __forceinline__ void operator()(long long i, int pos) const { rank_out[i] = pos; }
 };
-struct MovePair {
-    const unsigned long long* __restrict__ keys_in;
-    const int* __restrict__ idx_in;
-    unsigned long long* __restrict__ keys_out;
-    int* __restrict__ idx_out;
-    __device__ __forceinline__ void operator()(long long i, int pos) const {
-        keys_out[pos] = keys_in[i];
-        idx_out[pos] = idx_in[i];
-    }
-};
-
 template <typename KeyFn, typename Sink>
 __global__ void rank_emit_kernel(KeyFn keys, long long n, int n_keys,
                                  int seg_len, int n_segs, const int* __restrict__ table,
@@ -284,16 +263,6 @@ static int counting_rank(KeyFn keys, Sink sink, long long n, int n_keys, long lo
 int stable_rank_impl(const int* keys, long long n, int n_keys, int* rank_out,
                      long long* key_start, void* ws, size_t ws_bytes, cudaStream_t st) {
     return counting_rank(IntKeys{keys}, StoreRank{rank_out}, n, n_keys, key_start, ws, ws_bytes, st);
-}
-
-// one stable LSD radix pass over (64-bit key, int payload) pairs on the digit
-// (key >> shift) & (2^bits - 1); workspace as stable_rank_ws(n, 2^bits)
-int radix_pass_u64(const unsigned long long* keys_in, const int* idx_in, long long n, int shift,
-                   int bits, unsigned long long* keys_out, int* idx_out, long long* key_start,
-                   void* ws, size_t ws_bytes, cudaStream_t st) {
-    return counting_rank(DigitKeys{keys_in, shift, (1 << bits) - 1},
-                         MovePair{keys_in, idx_in, keys_out, idx_out}, n, 1 << bits, key_start,
-                         ws, ws_bytes, st);
 }
 
 size_t stable_rank_ws(long long n, int n_keys) {

@@ -493,6 +493,21 @@ def equalize(data, f, alpha):
     return out[:, :n].t().contiguous()
 
 
+def cml_nll(data, delta):
+    """The objective of ``cml`` (hic3defdr/util/dispersion.py:72-75) at
+    ``delta`` for (n, R) data -> float."""
+    data = np.asarray(data.cpu() if isinstance(data, torch.Tensor) else data,
+                      dtype=float)
+    n, r = data.shape
+    x = dev(np.ascontiguousarray(data.T))
+    out = torch.zeros(1, dtype=torch.float64, device='cuda')
+    wsb = lib().query('h3d_cml_nll_ws_bytes', n)
+    ws = workspace(wsb)
+    lib().call('h3d_cml_nll', ptr(x), n, n, r, float(delta), ptr(out),
+               ptr(ws), wsb, _stream())
+    return float(out.item())
+
+
 def _single_bin(data, f, estimator):
     data = np.asarray(data.cpu() if isinstance(data, torch.Tensor) else data,
                       dtype=float)

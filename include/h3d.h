@@ -231,6 +231,15 @@ int h3d_equalize(const double* x, const double* f, long long ld, long long n_px,
                  void* ws, size_t ws_bytes, h3d_stream_t stream);
 size_t h3d_equalize_ws_bytes(long long n_px);
 
+/* The objective of cml, hic3defdr/util/dispersion.py:72-75: conditional NB
+ * negative log-likelihood of one bin of (pseudo-)data, SoA (n_reps, ld), at
+ * delta = disp / (1 + disp), by the kernel the qCML driver launches (summed
+ * exactly in 128-bit fixed point).  nll_out: one double on the device. */
+int h3d_cml_nll(const double* data, long long ld, long long n_px, int n_reps,
+                double delta, double* nll_out, void* ws, size_t ws_bytes,
+                h3d_stream_t stream);
+size_t h3d_cml_nll_ws_bytes(long long n_px);
+
 /* lowess (lib5c.util.lowess.lowess as called at hic3defdr/util/lowess.py:72):
  * x sorted ascending, n points, returns fitted values y_fit (device). */
 int h3d_lowess(const double* x, const double* y, int n, double frac, int it,

@@ -16,7 +16,13 @@ parity failure.  Recorded (ref_config1.npz, < 10 MB):
   * disp_per_dist (D + 1, C), the fitted trends on the integer distances,
   * a seeded sample of 50 000 tested pixels per chromosome with every
     per-pixel output (disp, mu_hat_null, mu_hat_alt, llr, pvalues, qvalues),
-  * the number of pixels with q < 0.01 / 0.05 / 0.2 and the sum of q.
+  * the number of pixels with q < 0.01 / 0.05 / 0.2 and the sum of q,
+  * ``disp_selfnoise`` (D + 1, C): the reference's OWN reproducibility of
+    disp_per_dist -- the largest relative change of its qcml() result over
+    four random permutations of the pixel order inside the bin
+    (``--selfnoise``; the summation order of the likelihood changes Brent's
+    path).  Where the likelihood is flat (far distances, few counts) this
+    reaches 1e-6; the parity bar of a bin is max(1e-7, 3 x its self-noise).
 """
 import hashlib
 import os
@@ -63,7 +69,68 @@ def sample_index(n_d, chrom_index):
     return np.sort(rng.choice(n_d, size=min(N_SAMPLE, n_d), replace=False))
 
 
+_SN = {}
+
+
+def _selfnoise_task(task):
+    import warnings
+    from hic3defdr.util.dispersion import qcml as ref_qcml
+    d, c = task
+    sel = _SN['dist'] == d
+    if not sel.any():
+        return 0.0
+    reps = _SN['design'][:, c]
+    x, ff = _SN['raw'][sel][:, reps], _SN['f'][sel][:, reps]
+    rng = np.random.default_rng(100000 + 2 * d + c)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        base = ref_qcml(x, f=ff.copy())
+        assert base == _SN['dpd'][d, c], (d, c, base, _SN['dpd'][d, c])
+        worst = 0.0
+        for _ in range(4):
+            perm = rng.permutation(len(x))
+            v = ref_qcml(x[perm], f=ff[perm].copy())
+            worst = max(worst, abs(v - base) / base)
+    return worst
+
+
+def selfnoise():
+    """adds ``disp_selfnoise`` to the existing fixture (the reference's qcml on
+    every bin, 1 + 4 times; ~15 min on 8 cores)"""
+    import multiprocessing as mp
+    from oracle import pipeline as op
+    from hic3defdr_b200.synth import BASE_SEED, make_chrom
+    refrun.install()
+    path = os.path.join(HERE, 'ref_config1.npz')
+    g = dict(np.load(path))
+    design = np.array([[1, 0], [1, 0], [0, 1], [0, 1]], dtype=bool)
+    raws, fs, dists = [], [], []
+    for ci, c in enumerate(CHROMS):
+        mats, bias, _ = make_chrom(CHROMS[c], 4, DIST_MAX,
+                                   BASE_SEED + 1000 * 1 + 100 * ci, amp=300.0)
+        st = op.prepare_chrom(mats, bias, design, dist_max=DIST_MAX)
+        di = st['disp_idx']
+        row, col = st['row'][di], st['col'][di]
+        b = op.filter_bias(bias, 0.1)
+        fs.append(op.combined_factor(b, row, col, st['size_factors'][di]))
+        raws.append(st['raw'][di])
+        dists.append(col - row)
+    _SN.update(raw=np.concatenate(raws), f=np.concatenate(fs),
+               dist=np.concatenate(dists), design=design,
+               dpd=g['disp_per_dist'])
+    tasks = [(d, c) for d in range(DIST_MAX + 1) for c in range(2)]
+    with mp.get_context('fork').Pool(os.cpu_count()) as pool:
+        res = pool.map(_selfnoise_task, tasks, chunksize=4)
+    g['disp_selfnoise'] = np.array(res).reshape(DIST_MAX + 1, 2)
+    np.savez_compressed(path, **g)
+    sn = g['disp_selfnoise']
+    print('disp_selfnoise: median %.1e, 95%% %.1e, max %.1e'
+          % (np.median(sn), np.quantile(sn, 0.95), sn.max()))
+
+
 def main():
+    if '--selfnoise' in sys.argv:
+        return selfnoise()
     Ref = refrun.reference_class()
     root = tempfile.mkdtemp(dir=os.environ.get('TMPDIR', '/tmp'))
     kw = write_dataset(root, CHROMS, n_reps=4, dist_max=DIST_MAX, config=1,

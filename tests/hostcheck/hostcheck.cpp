@@ -3,7 +3,7 @@
 // checked against scipy on a machine without a GPU.  Never used by the product.
 #define H3D_HOST_STATS
 #include "../../hic3defdr_b200/csrc/h3d_math.cuh"
-H3dStats g_h3d_stats = {0, 0, 0, 0};
+H3dStats g_h3d_stats = {};
 extern "C" {
 void hc_fit_mu(const double* x, const double* b, const double* alpha, int n, int R,
                double* out, int* status) {
@@ -52,7 +52,9 @@ void hc_chi2_sf(const double* x, int n, int df, double* out) {
 void hc_stats(long long* out, int reset) {
     out[0] = g_h3d_stats.n_tail_eval; out[1] = g_h3d_stats.n_series_it;
     out[2] = g_h3d_stats.n_cf_it; out[3] = g_h3d_stats.n_q2q;
-    if (reset) g_h3d_stats = H3dStats{0, 0, 0, 0};
+    for (int k = 0; k < 16; ++k) out[4 + k] = g_h3d_stats.step_hist[k];
+    for (int k = 0; k < 8; ++k) out[20 + k] = g_h3d_stats.evals_hist[k];
+    if (reset) g_h3d_stats = H3dStats{};
 }
 // drives the Brent state machine with a callback
 typedef double (*hc_fn)(double);

@@ -280,3 +280,16 @@ def test_estimate_is_independent_of_pixel_order(estimator):
     assert np.isfinite(results[0]).sum() > 50
     np.testing.assert_array_equal(results[1], results[0])
     np.testing.assert_array_equal(results[2], results[0])
+
+
+def test_nll_device_vs_recorded_reference():
+    """nll_kernel (Stirling cores, table logarithm, exact 128-bit sum) against
+    the reference's objective -sum(gammaln ...) (util/dispersion.py:72-75)
+    recorded on the recorded pseudo-data at seven deltas across (1e-4,
+    100/101).  The reference's own value carries ~n * 3 gammaln roundings
+    (1e-16 * 1e3 each): 1e-12 relative."""
+    from hic3defdr_b200 import ops
+    s = load_stage_golden()
+    for delta, want in zip(s['nll_deltas'], s['nll_values']):
+        got = ops.cml_nll(s['equalize_0.01'], float(delta))
+        assert got == pytest.approx(float(want), rel=1e-12), delta
