@@ -44,11 +44,23 @@ SIGNATURES = {
     'h3d_loop_membership': (c_int, [vp, vp, vp, c_ll, vp, c_ll, vp, vp]),
     'h3d_gather_counts_factors': (c_int, [vp, vp, vp, c_ll, vp, vp, c_int, vp,
                                           c_int, vp, c_ll, vp, vp, vp, vp]),
+    'h3d_peer_alloc': (c_int, [c_sz, vp, vp]),
+    'h3d_peer_free': (c_int, [vp]),
+    'h3d_peer_open': (c_int, [vp, vp]),
+    'h3d_peer_close': (c_int, [vp]),
+    'h3d_pool_index': (c_int, [vp, vp, c_ll, c_int, vp, vp, vp]),
+    'h3d_pool_pull': (c_int, [vp, c_ll, vp, c_int, vp, vp, vp, vp, c_int, c_int,
+                              vp, c_int, c_ll, vp]),
     'h3d_stable_rank': (c_int, [vp, c_ll, c_int, vp, vp, vp, c_sz, vp]),
     'h3d_stable_rank_ws_bytes': (c_sz, [c_ll, c_int]),
     'h3d_estimate_dispersion': (c_int, [vp, vp, c_ll, vp, c_int, vp, c_int,
                                         c_int, c_int, vp, vp, vp, c_sz, vp]),
     'h3d_estimate_dispersion_ws_bytes': (c_sz, [c_ll, c_int, c_int, c_int]),
+    'h3d_estimate_dispersion_runs': (c_int, [vp, vp, c_ll, vp, vp, vp, c_int,
+                                             c_int, vp, c_int, c_int, c_int,
+                                             vp, vp, vp, c_sz, vp]),
+    'h3d_estimate_dispersion_runs_ws_bytes': (c_sz, [c_ll, c_int, c_int,
+                                                     c_int, c_int]),
     'h3d_equalize': (c_int, [vp, vp, c_ll, c_ll, c_int, c_dbl, vp, vp, vp,
                              c_sz, vp]),
     'h3d_equalize_ws_bytes': (c_sz, [c_ll]),
@@ -69,6 +81,7 @@ SIGNATURES = {
     'h3d_bh_ws_bytes': (c_sz, [c_ll]),
     'h3d_bh_ranked': (c_int, [vp, c_ll, c_ll, c_ll, vp, vp, vp, c_sz, vp]),
     'h3d_bh_apply_carry': (c_int, [vp, c_ll, c_dbl, vp]),
+    'h3d_bh_apply_carry_dev': (c_int, [vp, c_ll, vp, vp]),
     'h3d_connected_components': (c_int, [vp, vp, c_ll, vp, vp, vp, c_sz, vp]),
     'h3d_connected_components_ws_bytes': (c_sz, [c_ll]),
 }

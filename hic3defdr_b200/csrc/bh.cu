@@ -168,8 +168,10 @@ bh_finish_kernel(const unsigned long long* __restrict__ keys, const int* __restr
 // q <- min(q, carry), NaN kept (a distributed correction's contribution of
 // the buckets holding larger p-values)
 __global__ void __launch_bounds__(256)
-bh_apply_carry_kernel(double* __restrict__ q, long long n, double carry) {
+bh_apply_carry_kernel(double* __restrict__ q, long long n, double carry,
+                      const double* __restrict__ carry_dev) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (carry_dev) carry = *carry_dev;
     if (i < n) {
         const double v = q[i];
         if (v > carry) q[i] = carry;
@@ -201,7 +203,15 @@ extern "C" int h3d_bh(const double* p, long long n, double* q, void* ws, size_t 
 
 extern "C" int h3d_bh_apply_carry(double* q, long long n, double carry, h3d_stream_t stream) {
     if (n <= 0 || !(carry < 1.0)) return H3D_OK;      // q is already clipped at 1
-    bh_apply_carry_kernel<<<div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(q, n, carry);
+    bh_apply_carry_kernel<<<div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(q, n, carry, nullptr);
+    H3D_LAUNCHED("bh_apply_carry_kernel");
+    return H3D_OK;
+}
+
+extern "C" int h3d_bh_apply_carry_dev(double* q, long long n, const double* carry_dev,
+                                      h3d_stream_t stream) {
+    if (n <= 0) return H3D_OK;
+    bh_apply_carry_kernel<<<div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(q, n, 0.0, carry_dev);
     H3D_LAUNCHED("bh_apply_carry_kernel");
     return H3D_OK;
 }

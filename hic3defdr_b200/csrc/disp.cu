@@ -54,14 +54,14 @@ struct Problem {                 // one (segment, condition)
 
 struct Counters { int n_need_eq, n_in_brent, n_failed, n_fit_failed; };
 
-__global__ void init_problems_kernel(Problem* __restrict__ prob, const long long* __restrict__ seg_start,
+__global__ void init_problems_kernel(Problem* __restrict__ prob, const long long* __restrict__ seg_npx,
                                      int n_seg, int n_conds, int estimator, Counters* cnt) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p == 0) { cnt->n_need_eq = 0; cnt->n_in_brent = 0; cnt->n_failed = 0; cnt->n_fit_failed = 0; }
     if (p >= n_seg * n_conds) return;
     const int s = p / n_conds;
     Problem& q = prob[p];
-    q.n_px = seg_start[s + 1] - seg_start[s];
+    q.n_px = seg_npx[s];
     q.outer_iters = 0; q.nfev_total = 0;
     q.disp = (q.n_px > 0) ? 0.01 : NAN;                 // dispersion.py:33 / analysis.py:205
     q.status = (q.n_px > 0) ? ST_NEED_EQ : ST_EMPTY;
@@ -137,7 +137,7 @@ template <int MAXRC>
 __global__ void __launch_bounds__(256, H3D_EQ_MIN_BLOCKS)
 equalize_kernel(const double* __restrict__ x, const double* __restrict__ f, long long ld,
                 const int* __restrict__ chunk_seg, const long long* __restrict__ chunk_lo,
-                const long long* __restrict__ seg_start, CondReps cr, int estimator,
+                const long long* __restrict__ chunk_hi, CondReps cr, int estimator,
                 const Problem* __restrict__ prob, double* __restrict__ pseudo, Counters* cnt) {
     extern __shared__ unsigned char eq_smem[];
     EqTask* task = (EqTask*)eq_smem;                                    // [slot]
@@ -152,8 +152,7 @@ equalize_kernel(const double* __restrict__ x, const double* __restrict__ f, long
     if (q.status != ST_NEED_EQ) return;
     const double alpha = q.disp;
     const long long lo = chunk_lo[blockIdx.x];
-    const long long seg_hi = seg_start[s + 1];
-    const long long hi = (lo + kChunk < seg_hi) ? lo + kChunk : seg_hi;
+    const long long hi = chunk_hi[blockIdx.x];
     const int nr = cr.n_in[c];
     const int lane = threadIdx.x & 31;
     double* __restrict__ out_base = pseudo + (long long)cr.pseudo_row[c] * ld;
@@ -379,7 +378,7 @@ __device__ __forceinline__ void fix_atomic_add(Fix128* dst, const Fix128& t) {
 template <int MAXRC>
 __global__ void __launch_bounds__(256, H3D_NLL_MIN_BLOCKS)
 nll_kernel(const double* __restrict__ pseudo, long long ld, const int* __restrict__ chunk_seg,
-           const long long* __restrict__ chunk_lo, const long long* __restrict__ seg_start,
+           const long long* __restrict__ chunk_lo, const long long* __restrict__ chunk_hi,
            CondReps cr, const Problem* __restrict__ prob, Fix128* __restrict__ acc) {
     __shared__ Fix128 sh[8];
     const int c = blockIdx.y;
@@ -393,8 +392,7 @@ nll_kernel(const double* __restrict__ pseudo, long long ld, const int* __restric
     const double cst = lgamma_pos(nrr) - (double)nr * lgamma_pos(r) +
                        (double)(nr - 1) * 0.9189385332046727;
     const long long lo = chunk_lo[blockIdx.x];
-    const long long seg_hi = seg_start[s + 1];
-    const long long hi = (lo + kChunk < seg_hi) ? lo + kChunk : seg_hi;
+    const long long hi = chunk_hi[blockIdx.x];
     const double* __restrict__ base = pseudo + (long long)cr.pseudo_row[c] * ld;
     FixAcc a = {0ull, 0ll, 0};
     if (r >= 10.0) {
@@ -438,13 +436,12 @@ template <int MAXRC>
 __global__ void __launch_bounds__(256)
 mme_kernel(const double* __restrict__ x, const double* __restrict__ f, long long ld,
            const int* __restrict__ chunk_seg, const long long* __restrict__ chunk_lo,
-           const long long* __restrict__ seg_start, CondReps cr, Fix128* __restrict__ acc) {
+           const long long* __restrict__ chunk_hi, CondReps cr, Fix128* __restrict__ acc) {
     __shared__ Fix128 sh[8];
     const int c = blockIdx.y;
     const int s = chunk_seg[blockIdx.x];
     const long long lo = chunk_lo[blockIdx.x];
-    const long long seg_hi = seg_start[s + 1];
-    const long long hi = (lo + kChunk < seg_hi) ? lo + kChunk : seg_hi;
+    const long long hi = chunk_hi[blockIdx.x];
     const int nr = cr.n_in[c];
     FixAcc a = {0ull, 0ll, 0};
     int n_est = 0;
@@ -608,12 +605,6 @@ struct EventPool {
     ~EventPool() { for (cudaEvent_t e : ev) if (e) cudaEventDestroy(e); }
 };
 
-static long long count_chunks(const long long* seg_start_host, int n_seg) {
-    long long n = 0;
-    for (int s = 0; s < n_seg; ++s) n += (seg_start_host[s + 1] - seg_start_host[s] + kChunk - 1) / kChunk;
-    return n;
-}
-
 static int make_cond_reps(const unsigned char* design_host, int n_reps, int n_conds, CondReps* cr,
                           int* rows_out, int* max_rc_out) {
     cr->n_conds = n_conds;
@@ -632,31 +623,46 @@ static int make_cond_reps(const unsigned char* design_host, int n_reps, int n_co
     return H3D_OK;
 }
 
-// chunk tables of the segments, built on the host and copied
-struct ChunkTables { int n_chunks; int* chunk_seg; long long* chunk_lo; long long* seg_start; };
-static int make_chunk_tables(const long long* seg_start_host, int n_seg, Workspace& w, cudaStream_t st,
-                             ChunkTables* t) {
-    const long long n_chunks_ll = count_chunks(seg_start_host, n_seg);
+// Chunk tables, built on the host and copied.  A segment (one distance) is a
+// list of runs [lo, hi) of the pooled arrays -- one run in a one-process
+// estimate, one run per source rank after a multi-GPU exchange (the likelihood
+// sums do not depend on the pixel order, so the runs need not be regrouped) --
+// and every run is cut into chunks of at most kChunk pixels.
+struct ChunkTables { int n_chunks; int* chunk_seg; long long *chunk_lo, *chunk_hi, *seg_npx; };
+static int make_chunk_tables(const int* run_seg, const long long* run_lo, const long long* run_hi,
+                             int n_runs, int n_seg, Workspace& w, cudaStream_t st, ChunkTables* t) {
+    long long n_chunks_ll = 0;
+    for (int r = 0; r < n_runs; ++r) {
+        H3D_REQUIRE(run_seg[r] >= 0 && run_seg[r] < n_seg && run_hi[r] >= run_lo[r] && run_lo[r] >= 0,
+                    "malformed run");
+        n_chunks_ll += (run_hi[r] - run_lo[r] + kChunk - 1) / kChunk;
+    }
     H3D_REQUIRE(n_chunks_ll < 2147483647LL, "too many chunks");
     const int n_chunks = (int)n_chunks_ll;
     std::vector<int> h_chunk_seg(n_chunks);
-    std::vector<long long> h_chunk_lo(n_chunks);
+    std::vector<long long> h_chunk_lo(n_chunks), h_chunk_hi(n_chunks), h_seg_npx(n_seg, 0);
     int k = 0;
-    for (int s = 0; s < n_seg; ++s)
-        for (long long lo = seg_start_host[s]; lo < seg_start_host[s + 1]; lo += kChunk) {
-            h_chunk_seg[k] = s; h_chunk_lo[k] = lo; ++k;
+    for (int r = 0; r < n_runs; ++r) {
+        h_seg_npx[run_seg[r]] += run_hi[r] - run_lo[r];
+        for (long long lo = run_lo[r]; lo < run_hi[r]; lo += kChunk) {
+            h_chunk_seg[k] = run_seg[r]; h_chunk_lo[k] = lo;
+            h_chunk_hi[k] = (lo + kChunk < run_hi[r]) ? lo + kChunk : run_hi[r];
+            ++k;
         }
+    }
     t->n_chunks = n_chunks;
     t->chunk_seg = w.take<int>(n_chunks);
     t->chunk_lo = w.take<long long>(n_chunks);
-    t->seg_start = w.take<long long>(n_seg + 1);
-    if (!t->chunk_seg || !t->chunk_lo || !t->seg_start) {
+    t->chunk_hi = w.take<long long>(n_chunks);
+    t->seg_npx = w.take<long long>(n_seg);
+    if (!t->chunk_seg || !t->chunk_lo || !t->chunk_hi || !t->seg_npx) {
         set_error("dispersion workspace too small (%zu bytes given)", w.size);
         return H3D_ERR_WORKSPACE;
     }
     H3D_CHECK(cudaMemcpyAsync(t->chunk_seg, h_chunk_seg.data(), (size_t)n_chunks * 4, cudaMemcpyHostToDevice, st));
     H3D_CHECK(cudaMemcpyAsync(t->chunk_lo, h_chunk_lo.data(), (size_t)n_chunks * 8, cudaMemcpyHostToDevice, st));
-    H3D_CHECK(cudaMemcpyAsync(t->seg_start, seg_start_host, (size_t)(n_seg + 1) * 8, cudaMemcpyHostToDevice, st));
+    H3D_CHECK(cudaMemcpyAsync(t->chunk_hi, h_chunk_hi.data(), (size_t)n_chunks * 8, cudaMemcpyHostToDevice, st));
+    H3D_CHECK(cudaMemcpyAsync(t->seg_npx, h_seg_npx.data(), (size_t)n_seg * 8, cudaMemcpyHostToDevice, st));
     // the host vectors must outlive the async copies
     H3D_CHECK(cudaStreamSynchronize(st));
     return H3D_OK;
@@ -676,16 +682,25 @@ static int set_equalize_smem(size_t eq_smem) {
     else if (max_rc <= 8) { CALL(8); }          \
     else { CALL(16); }
 
-extern "C" size_t h3d_estimate_dispersion_ws_bytes(long long n_px, int n_seg, int n_reps, int n_conds) {
-    const long long max_chunks = n_px / kChunk + n_seg + 1;
+static size_t disp_ws_bytes(long long n_px, int n_runs, int n_seg, int n_reps, int n_conds) {
+    const long long max_chunks = n_px / kChunk + n_runs + 1;
     size_t b = 0;
     b += ws_pad((size_t)n_reps * n_conds * n_px * 8);               // pseudo (worst case)
-    b += ws_pad((size_t)max_chunks * 4) + ws_pad((size_t)max_chunks * 8);
+    b += ws_pad((size_t)max_chunks * 4) + 2 * ws_pad((size_t)max_chunks * 8);
     b += ws_pad((size_t)(n_seg + 1) * 8);
     b += ws_pad((size_t)n_seg * n_conds * sizeof(Problem));
     b += ws_pad((size_t)n_seg * n_conds * sizeof(Fix128));
     b += ws_pad((size_t)n_seg * n_conds * 8) + ws_pad(64) + ws_pad(64);
     return b;
+}
+
+extern "C" size_t h3d_estimate_dispersion_ws_bytes(long long n_px, int n_seg, int n_reps, int n_conds) {
+    return disp_ws_bytes(n_px, n_seg, n_seg, n_reps, n_conds);
+}
+
+extern "C" size_t h3d_estimate_dispersion_runs_ws_bytes(long long n_px, int n_runs, int n_seg, int n_reps,
+                                                        int n_conds) {
+    return disp_ws_bytes(n_px, n_runs, n_seg, n_reps, n_conds);
 }
 
 // rounds the host keeps queued ahead of the last round whose counters it has seen
@@ -701,6 +716,22 @@ extern "C" int h3d_estimate_dispersion(const double* x, const double* f, long lo
                                        int estimator, double* disp_per_dist_host,
                                        long long* stats_host, void* ws, size_t ws_bytes,
                                        h3d_stream_t stream) {
+    H3D_REQUIRE(n_seg >= 1, "no segments");
+    H3D_REQUIRE(seg_start_host[0] == 0, "segments must start at 0");
+    std::vector<int> run_seg(n_seg);
+    for (int s = 0; s < n_seg; ++s) run_seg[s] = s;
+    return h3d_estimate_dispersion_runs(x, f, ld, run_seg.data(), seg_start_host, seg_start_host + 1,
+                                        n_seg, n_seg, design_host, n_reps, n_conds, estimator,
+                                        disp_per_dist_host, stats_host, ws, ws_bytes, stream);
+}
+
+extern "C" int h3d_estimate_dispersion_runs(const double* x, const double* f, long long ld,
+                                            const int* run_seg_host, const long long* run_lo_host,
+                                            const long long* run_hi_host, int n_runs, int n_seg,
+                                            const unsigned char* design_host, int n_reps, int n_conds,
+                                            int estimator, double* disp_per_dist_host,
+                                            long long* stats_host, void* ws, size_t ws_bytes,
+                                            h3d_stream_t stream) {
     H3D_REQUIRE(n_reps >= 1 && n_reps <= H3D_MAX_REPS, "n_reps out of range");
     H3D_REQUIRE(n_conds >= 1 && n_conds <= H3D_MAX_CONDS, "n_conds out of range");
     H3D_REQUIRE(estimator >= 0 && estimator <= 2, "unknown estimator");
@@ -710,8 +741,11 @@ extern "C" int h3d_estimate_dispersion(const double* x, const double* f, long lo
     CondReps cr;
     int rows = 0, max_rc = 0;
     { int rc = make_cond_reps(design_host, n_reps, n_conds, &cr, &rows, &max_rc); if (rc) return rc; }
-    const long long n_px = seg_start_host[n_seg] - seg_start_host[0];
-    H3D_REQUIRE(seg_start_host[0] == 0 && n_px <= ld, "segments must start at 0 and fit in ld");
+    long long n_px = 0;
+    for (int r = 0; r < n_runs; ++r) {
+        H3D_REQUIRE(run_hi_host[r] <= ld, "runs must fit in ld");
+        n_px += run_hi_host[r] - run_lo_host[r];
+    }
     const int n_prob = n_seg * n_conds;
     for (int p = 0; p < n_prob; ++p) disp_per_dist_host[p] = NAN;
     if (stats_host) for (int k = 0; k < 9; ++k) stats_host[k] = 0;
@@ -719,7 +753,7 @@ extern "C" int h3d_estimate_dispersion(const double* x, const double* f, long lo
 
     Workspace w(ws, ws_bytes);
     ChunkTables ct;
-    { int rc = make_chunk_tables(seg_start_host, n_seg, w, st, &ct); if (rc) return rc; }
+    { int rc = make_chunk_tables(run_seg_host, run_lo_host, run_hi_host, n_runs, n_seg, w, st, &ct); if (rc) return rc; }
     const int n_chunks = ct.n_chunks;
     double* pseudo = w.take<double>((size_t)rows * ld);
     Problem* prob = w.take<Problem>(n_prob);
@@ -734,7 +768,7 @@ extern "C" int h3d_estimate_dispersion(const double* x, const double* f, long lo
     H3D_CHECK(cudaMemsetAsync(acc, 0, (size_t)n_prob * sizeof(Fix128), st));
 
     const int pgrid = div_up(n_prob, 128);
-    init_problems_kernel<<<pgrid, 128, 0, st>>>(prob, ct.seg_start, n_seg, n_conds, estimator, cnt);
+    init_problems_kernel<<<pgrid, 128, 0, st>>>(prob, ct.seg_npx, n_seg, n_conds, estimator, cnt);
     H3D_LAUNCHED("init_problems_kernel");
     const dim3 cgrid(n_chunks, n_conds);
     const int ahead = qcml_run_ahead();
@@ -759,7 +793,7 @@ extern "C" int h3d_estimate_dispersion(const double* x, const double* f, long lo
     long long eq_launches = 0, nll_launches = 0;
 
     if (estimator == H3D_EST_MME) {
-#define CALL(M) mme_kernel<M><<<cgrid, 256, 0, st>>>(x, f, ld, ct.chunk_seg, ct.chunk_lo, ct.seg_start, cr, acc)
+#define CALL(M) mme_kernel<M><<<cgrid, 256, 0, st>>>(x, f, ld, ct.chunk_seg, ct.chunk_lo, ct.chunk_hi, cr, acc)
         DISPATCH_RC(CALL)
 #undef CALL
         H3D_LAUNCHED("mme_kernel");
@@ -782,13 +816,13 @@ extern "C" int h3d_estimate_dispersion(const double* x, const double* f, long lo
             while (launched - seen < ahead) {
                 cudaEvent_t* ev = &evp.ev[4 * (launched % ring)];
                 H3D_CHECK(cudaEventRecord(ev[0], st));
-#define CALL(M) equalize_kernel<M><<<cgrid, 256, eq_smem, st>>>(x, f, ld, ct.chunk_seg, ct.chunk_lo, ct.seg_start, cr, \
+#define CALL(M) equalize_kernel<M><<<cgrid, 256, eq_smem, st>>>(x, f, ld, ct.chunk_seg, ct.chunk_lo, ct.chunk_hi, cr, \
         estimator, prob, pseudo, cnt)
                 DISPATCH_RC(CALL)
 #undef CALL
                 H3D_LAUNCHED("equalize_kernel");
                 H3D_CHECK(cudaEventRecord(ev[1], st));
-#define CALL(M) nll_kernel<M><<<cgrid, 256, 0, st>>>(pseudo, ld, ct.chunk_seg, ct.chunk_lo, ct.seg_start, cr, prob, acc)
+#define CALL(M) nll_kernel<M><<<cgrid, 256, 0, st>>>(pseudo, ld, ct.chunk_seg, ct.chunk_lo, ct.chunk_hi, cr, prob, acc)
                 DISPATCH_RC(CALL)
 #undef CALL
                 H3D_LAUNCHED("nll_kernel");
@@ -875,7 +909,7 @@ extern "C" int h3d_estimate_dispersion(const double* x, const double* f, long lo
 // element by element with the reference's.
 extern "C" size_t h3d_equalize_ws_bytes(long long n_px) {
     const long long max_chunks = n_px / kChunk + 2;
-    return ws_pad((size_t)max_chunks * 4) + ws_pad((size_t)max_chunks * 8) + ws_pad(16) +
+    return ws_pad((size_t)max_chunks * 4) + 2 * ws_pad((size_t)max_chunks * 8) + ws_pad(16) +
            ws_pad(sizeof(Problem)) + ws_pad(64);
 }
 
@@ -891,9 +925,10 @@ extern "C" int h3d_equalize(const double* x, const double* f, long long ld, long
     int rows = 0, max_rc = 0;
     { int rc = make_cond_reps(design.data(), n_reps, 1, &cr, &rows, &max_rc); if (rc) return rc; }
     const long long seg[2] = {0, n_px};
+    const int seg0 = 0;
     Workspace w(ws, ws_bytes);
     ChunkTables ct;
-    { int rc = make_chunk_tables(seg, 1, w, st, &ct); if (rc) return rc; }
+    { int rc = make_chunk_tables(&seg0, seg, seg + 1, 1, 1, w, st, &ct); if (rc) return rc; }
     Problem* prob = w.take<Problem>(1);
     Counters* cnt = w.take<Counters>(1);
     if (!prob || !cnt) { set_error("equalize workspace too small (%zu bytes given)", ws_bytes); return H3D_ERR_WORKSPACE; }
@@ -902,7 +937,7 @@ extern "C" int h3d_equalize(const double* x, const double* f, long long ld, long
     const size_t eq_smem = (size_t)kEqTasks * (sizeof(EqTask) + 2 * sizeof(int));
     { int rc = set_equalize_smem(eq_smem); if (rc) return rc; }
     const dim3 cgrid(ct.n_chunks, 1);
-#define CALL(M) equalize_kernel<M><<<cgrid, 256, eq_smem, st>>>(x, f, ld, ct.chunk_seg, ct.chunk_lo, ct.seg_start, cr, \
+#define CALL(M) equalize_kernel<M><<<cgrid, 256, eq_smem, st>>>(x, f, ld, ct.chunk_seg, ct.chunk_lo, ct.chunk_hi, cr, \
         H3D_EST_QCML, prob, pseudo_out, cnt)
     DISPATCH_RC(CALL)
 #undef CALL
@@ -931,9 +966,10 @@ extern "C" int h3d_cml_nll(const double* data, long long ld, long long n_px, int
     int rows = 0, max_rc = 0;
     { int rc = make_cond_reps(design.data(), n_reps, 1, &cr, &rows, &max_rc); if (rc) return rc; }
     const long long seg[2] = {0, n_px};
+    const int seg0 = 0;
     Workspace w(ws, ws_bytes);
     ChunkTables ct;
-    { int rc = make_chunk_tables(seg, 1, w, st, &ct); if (rc) return rc; }
+    { int rc = make_chunk_tables(&seg0, seg, seg + 1, 1, 1, w, st, &ct); if (rc) return rc; }
     Problem* prob = w.take<Problem>(1);
     Counters* cnt = w.take<Counters>(1);
     Fix128* acc = w.take<Fix128>(1);
@@ -942,7 +978,7 @@ extern "C" int h3d_cml_nll(const double* data, long long ld, long long n_px, int
     single_bin_problems_kernel<<<1, 32, 0, st>>>(prob, 1, n_px, 0.0, delta, ST_IN_BRENT, cnt);
     H3D_LAUNCHED("single_bin_problems_kernel");
     const dim3 cgrid(ct.n_chunks, 1);
-#define CALL(M) nll_kernel<M><<<cgrid, 256, 0, st>>>(data, ld, ct.chunk_seg, ct.chunk_lo, ct.seg_start, cr, prob, acc)
+#define CALL(M) nll_kernel<M><<<cgrid, 256, 0, st>>>(data, ld, ct.chunk_seg, ct.chunk_lo, ct.chunk_hi, cr, prob, acc)
     DISPATCH_RC(CALL)
 #undef CALL
     H3D_LAUNCHED("nll_kernel");

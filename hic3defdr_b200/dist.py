@@ -177,41 +177,174 @@ def owned_distances(n_dist, me=None, n_ranks=None):
 def exchange_by_distance(x, f, seg_start, n_local):
     """x, f: (R, ld) pooled on this rank in ``distance_keys`` order;
     seg_start: (ws * per + 1) local group boundaries over the keys.  Returns
-    (x, f, seg_start) holding ALL ranks' pixels of the distances this rank
-    owns, one segment per owned key (``per`` segments, the trailing ones empty
-    when the distances do not divide evenly)."""
+    (x, f, runs): the arrays hold ALL ranks' pixels of the distances this rank
+    owns, ``runs`` = (run_seg, run_lo, run_hi) int arrays describing where:
+    run r is the pixels [run_lo[r], run_hi[r]) of owned distance run_seg[r]
+    (``per`` owned keys, the trailing ones empty when the distances do not
+    divide evenly).  A distance's pixels arrive as one run per source rank, in
+    rank order, and stay where they land: the dispersion kernels sum a bin
+    exactly, whatever its pixel order (ops.estimate_dispersion, ``runs=``).
+
+    One grouped set of point-to-point transfers (a single NCCL group: every
+    replicate row of x and f, to and from every peer) instead of one collective
+    per row."""
     ws, me = world_size(), rank()
+    n_keys = len(seg_start) - 1
     if ws == 1:
-        return x, f, seg_start
-    per = (len(seg_start) - 1) // ws
+        seg = np.asarray(seg_start, dtype=np.int64)
+        return x, f, (np.arange(n_keys, dtype=np.int32), seg[:-1].copy(),
+                      seg[1:].copy())
+    per = n_keys // ws
     local_counts = np.diff(seg_start)
     all_counts = _all_gather_counts(local_counts)          # (ws, ws * per)
     n_reps = x.shape[0]
-    send_splits = [int(seg_start[(k + 1) * per] - seg_start[k * per])
-                   for k in range(ws)]
+    soff = np.asarray(seg_start, dtype=np.int64)[::per]     # (ws + 1,) send offsets
     recv_counts = all_counts[:, me * per:(me + 1) * per]    # (ws, per)
-    recv_splits = [int(c.sum()) for c in recv_counts]
-    n_recv = int(sum(recv_splits))
+    roff = np.concatenate([[0], np.cumsum(recv_counts.sum(axis=1))]) \
+        .astype(np.int64)                                   # (ws + 1,) receive offsets
+    n_recv = int(roff[-1])
     xr = torch.empty((n_reps, max(n_recv, 1)), dtype=x.dtype, device=x.device)
     fr = torch.empty_like(xr)
-    works = []
-    for r in range(n_reps):
-        for src, dst in ((x, xr), (f, fr)):
-            works.append(td.all_to_all_single(
-                dst[r, :n_recv], src[r, :n_local],
-                output_split_sizes=recv_splits, input_split_sizes=send_splits,
-                async_op=True))
-    pos = regroup_positions(recv_counts, x.device)
-    for w in works:
-        w.wait()
-    xo = torch.empty_like(xr)
-    fo = torch.empty_like(fr)
-    if n_recv:                  # pos is a permutation: a plain indexed copy
-        xo.index_copy_(1, pos, xr[:, :n_recv])
-        fo.index_copy_(1, pos, fr[:, :n_recv])
-    seg = np.concatenate([[0], np.cumsum(recv_counts.sum(axis=0))]) \
-        .astype(np.int64)
-    return xo, fo, seg
+    p2p = []
+    for src, dst in ((x, xr), (f, fr)):
+        a, b = int(soff[me]), int(soff[me + 1])
+        if b > a:                                   # this rank's own share
+            dst[:, int(roff[me]):int(roff[me + 1])].copy_(src[:, a:b])
+        for r in range(n_reps):
+            for k in range(ws):
+                if k == me:
+                    continue
+                a, b = int(soff[k]), int(soff[k + 1])
+                if b > a:
+                    p2p.append(td.P2POp(td.isend, src[r, a:b], k))
+                a, b = int(roff[k]), int(roff[k + 1])
+                if b > a:
+                    p2p.append(td.P2POp(td.irecv, dst[r, a:b], k))
+    if p2p:
+        for req in td.batch_isend_irecv(p2p):
+            req.wait()
+    # run (s, j): source rank s, owned key j
+    lo = roff[:-1, None] + np.cumsum(recv_counts, axis=1) - recv_counts
+    hi = lo + recv_counts
+    seg_of = np.broadcast_to(np.arange(per, dtype=np.int32)[None, :],
+                             recv_counts.shape)
+    order = np.argsort(seg_of.ravel(), kind='stable')       # by key, then source
+    runs = (np.ascontiguousarray(seg_of.ravel()[order].astype(np.int32)),
+            np.ascontiguousarray(lo.ravel()[order].astype(np.int64)),
+            np.ascontiguousarray(hi.ravel()[order].astype(np.int64)))
+    return xr, fr, runs
+
+
+def owner_layout(all_counts, per, me):
+    """Where every rank's pooled pixels live after the exchange by distance
+    owner.  ``all_counts``: (ws, ws * per) pixels per (source rank, key), key =
+    owner * per + owned index (``distance_keys``).  The buffer of owner k holds
+    one run per (source s, owned key j), source-major:
+    ``lo_k[s, j] = sum(counts[:s, k's keys]) + sum(counts[s, k's keys before j])``.
+    Returns (n_recv (ws,), shift (ws * per,), runs): n_recv[k] = pixels owner k
+    receives; shift[key] = position of THIS rank's first pixel of ``key`` in
+    its owner's buffer minus its position in this rank's own pooled order (so a
+    pixel at local pooled position p goes to p + shift[key]); runs = (run_seg,
+    run_lo, run_hi) of THIS rank's buffer, ordered by key, then source."""
+    c = np.asarray(all_counts, dtype=np.int64)
+    ws = c.shape[0]
+    blocks = c.reshape(ws, ws, per)                         # [source, owner, j]
+    n_recv = blocks.sum(axis=(0, 2))                        # (ws,)
+    per_src = blocks.sum(axis=2)                            # [source, owner]
+    src_off = np.cumsum(per_src, axis=0) - per_src          # [source, owner]
+    within = np.cumsum(blocks, axis=2) - blocks             # [source, owner, j]
+    lo = src_off[:, :, None] + within                       # [source, owner, j]
+    local_start = np.cumsum(c[me]) - c[me]                  # (ws * per,)
+    shift = lo[me].reshape(-1) - local_start
+    mine_lo = lo[:, me, :]                                  # [source, j]
+    mine_cnt = blocks[:, me, :]
+    seg_of = np.broadcast_to(np.arange(per, dtype=np.int32)[None, :],
+                             mine_cnt.shape)
+    order = np.argsort(seg_of.ravel(), kind='stable')
+    runs = (np.ascontiguousarray(seg_of.ravel()[order].astype(np.int32)),
+            np.ascontiguousarray(mine_lo.ravel()[order]),
+            np.ascontiguousarray((mine_lo + mine_cnt).ravel()[order]))
+    return n_recv, shift, runs
+
+
+class RawMatrix(object):
+    """a (rows, ld) float64 matrix in device memory that torch did not
+    allocate (a peer-shared receive buffer): just what the C-ABI calls need"""
+
+    def __init__(self, address, shape):
+        self.address, self.shape = int(address), tuple(shape)
+
+    def data_ptr(self):
+        return self.address
+
+
+class PeerBuffers(object):
+    """This rank's receive buffer for the distance exchange and the other
+    ranks' buffers opened through CUDA IPC (include/h3d.h, h3d_peer_*).  The
+    buffer persists across steps and only grows; every rank calls ``ensure``
+    with the same size at the same point."""
+
+    def __init__(self):
+        self.nbytes, self.own, self.ptrs = 0, None, None
+
+    def ensure(self, nbytes):
+        import ctypes
+        from hic3defdr_b200._native import lib
+        if nbytes <= self.nbytes:
+            return self.ptrs
+        self.release()
+        nbytes = int(nbytes * 1.25) // 4096 * 4096 + 4096
+        own = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * 64)()
+        lib().call('h3d_peer_alloc', nbytes, ctypes.byref(own), handle)
+        handles = [None] * world_size()
+        td.all_gather_object(handles, bytes(handle))
+        ptrs = []
+        for k, h in enumerate(handles):
+            if k == rank():
+                ptrs.append(own.value)
+                continue
+            p = ctypes.c_void_p()
+            lib().call('h3d_peer_open',
+                       (ctypes.c_ubyte * 64).from_buffer_copy(h),
+                       ctypes.byref(p))
+            ptrs.append(p.value)
+        self.nbytes, self.own, self.ptrs = nbytes, own.value, ptrs
+        barrier()
+        return ptrs
+
+    def release(self):
+        from hic3defdr_b200._native import lib
+        if self.own is None:
+            return
+        torch.cuda.synchronize()
+        barrier()                       # nobody still writes into a buffer
+        for k, p in enumerate(self.ptrs):
+            if k != rank():
+                lib().call('h3d_peer_close', p)
+        barrier()                       # every mapping is closed before the free
+        lib().call('h3d_peer_free', self.own)
+        self.nbytes, self.own, self.ptrs = 0, None, None
+
+
+_PEERS = PeerBuffers()
+
+
+def peer_exchange_enabled():
+    """The pooling gather writes straight into the owners' buffers over
+    NVLink (csrc/peer.cu) when the ranks run NCCL on one node; ``H3D_EXCHANGE=
+    nccl`` selects the grouped point-to-point transfers instead."""
+    import os
+    return initialized() and world_size() > 1 and \
+        td.get_backend() == 'nccl' and \
+        os.environ.get('H3D_EXCHANGE', 'peer') == 'peer'
+
+
+def fence_peer_writes():
+    """every rank's peer writes issued so far (stream order) have landed when
+    this returns on the stream: a one-element all-reduce"""
+    t = torch.zeros(1, dtype=torch.int32, device='cuda')
+    td.all_reduce(t)
 
 
 def merge_disp_per_dist(disp_owned, n_dist):
@@ -258,15 +391,15 @@ def sample_positions(n, take, device=None):
 
 def _partition(bucket, n_buckets):
     """Stable partition by bucket id: (position of every element in
-    bucket-major order, bucket sizes as a host int64 array)."""
+    bucket-major order, bucket sizes as an int64 tensor on the same device)."""
     if bucket.is_cuda:
         from hic3defdr_b200 import ops
         pos, start = ops.stable_rank(bucket, n_buckets)
-        return pos.long(), np.diff(start.cpu().numpy())
+        return pos.long(), start[1:] - start[:-1]
     order = torch.argsort(bucket, stable=True)
     pos = torch.empty_like(order)
     pos[order] = torch.arange(len(order))
-    return pos, np.bincount(bucket.numpy(), minlength=n_buckets).astype(np.int64)
+    return pos, torch.bincount(bucket.long(), minlength=n_buckets)
 
 
 def global_bh(local_p, bh_fn=None, bh_ranked_fn=None, carry_fn=None):
@@ -280,7 +413,8 @@ def global_bh(local_p, bh_fn=None, bh_ranked_fn=None, carry_fn=None):
     p n / rank and the running minimum inside the bucket; the bucket minima
     (one double per rank) are all-gathered for the carry across buckets; the
     q-values return by the mirrored all-to-all.  Equal p-values always land in
-    the same bucket, so the result is identical to the single-process one."""
+    the same bucket, so the result is identical to the single-process one.
+    The host waits for the device once (the all-to-all split sizes)."""
     if bh_fn is None:
         from hic3defdr_b200 import ops
         bh_fn, bh_ranked_fn, carry_fn = ops.adjust_pvalues, \
@@ -291,30 +425,36 @@ def global_bh(local_p, bh_fn=None, bh_ranked_fn=None, carry_fn=None):
     n = local_p.numel()
     device = local_p.device
     finite = torch.isfinite(local_p)
-    # splitters: evenly strided local sample of the finite values
-    fin_vals = local_p[finite]
-    n_fin = fin_vals.numel()
+    # splitters: evenly strided local sample of the finite values (a stable
+    # partition brings them to the front; no host round trip for their count)
+    fpos, fsizes = _partition((~finite).to(torch.int32), 2)
+    n_fin_t = fsizes[0]
     sample = torch.full((BH_SAMPLES,), float('inf'), dtype=local_p.dtype,
                         device=device)
-    if n_fin:
-        take = min(BH_SAMPLES, n_fin)
-        sel = sample_positions(n_fin, take, device)
-        sample[:take] = fin_vals[sel]
-    gathered = [torch.empty_like(sample) for _ in range(ws)]
-    td.all_gather(gathered, sample)
-    allsamp = torch.sort(torch.cat(gathered)).values
-    n_samp = int(torch.isfinite(allsamp).sum().item())
-    cut = [min(max(n_samp * k // ws, 0), max(n_samp - 1, 0))
-           for k in range(1, ws)]
-    splitters = allsamp[torch.tensor(cut, dtype=torch.long, device=device)]
+    if n:
+        fin_first = torch.empty_like(local_p)
+        fin_first[fpos] = local_p
+        k = torch.arange(BH_SAMPLES, dtype=torch.int64, device=device)
+        take = torch.clamp(n_fin_t, max=BH_SAMPLES)
+        sel = (k * torch.clamp(n_fin_t - 1, min=0)) // \
+            torch.clamp(take - 1, min=1)
+        vals = fin_first[torch.clamp(sel, max=max(n - 1, 0))]
+        sample = torch.where(k < take, vals, sample)
+    gathered = _all_gather_flat(sample)
+    allsamp = torch.sort(gathered.view(-1)).values
+    n_samp = torch.isfinite(allsamp).sum()
+    cut = torch.clamp((n_samp * torch.arange(1, ws, device=device)) // ws,
+                      max=None, min=0)
+    cut = torch.minimum(cut, torch.clamp(n_samp - 1, min=0))
+    splitters = allsamp[cut]
     # bucket of every local value (non-finite: last bucket), stable partition
     bucket = torch.bucketize(local_p, splitters).to(torch.int32)
     bucket = torch.where(finite, bucket, torch.full_like(bucket, ws - 1))
     pos, sizes = _partition(bucket, ws)
     send = torch.empty_like(local_p)
     send[pos] = local_p
-    info = np.concatenate([sizes, [n_fin]])
-    table = _all_gather_counts(info)                 # (ws, ws + 1)
+    info = torch.cat([sizes.to(torch.int64), n_fin_t.to(torch.int64).view(1)])
+    table = _all_gather_flat(info).cpu().numpy()     # (ws, ws + 1): the one sync
     counts, n_total = table[:, :ws], int(table[:, ws].sum())
     send_splits = [int(v) for v in counts[me]]
     recv_splits = [int(v) for v in counts[:, me]]
@@ -325,8 +465,9 @@ def global_bh(local_p, bh_fn=None, bh_ranked_fn=None, carry_fn=None):
     # lower buckets are counts of finite values
     rank_offset = int(counts[:, :me].sum())
     q_bucket, bmin = bh_ranked_fn(recv, rank_offset, n_total)
-    higher = _all_gather_flat(bmin).cpu().numpy().ravel()[me + 1:]
-    carry = float(higher.min()) if len(higher) else float('inf')
+    mins = _all_gather_flat(bmin.view(1)).view(-1)
+    inf = torch.full((1,), float('inf'), dtype=mins.dtype, device=mins.device)
+    carry = torch.cat([mins[me + 1:], inf]).min()       # stays on the device
     q_bucket = carry_fn(q_bucket, carry)
     back = torch.empty_like(send)
     td.all_to_all_single(back, q_bucket, output_split_sizes=send_splits,

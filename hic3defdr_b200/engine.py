@@ -47,6 +47,8 @@ def prepare_chrom_steps(csr, bias_raw, design, dist_min=4, dist_max=200,
     n_d = int((yield pending)[0])
     st.update(size_factors=sf, scaled=scaled, disp_idx=disp_idx,
               disp_index=index[:n_d])
+    if table.dim() == 2:
+        st['sf_table'] = table          # (D + 1, R): size_factors = table[dist]
     if loop_pixels is not None:
         st['loop_idx'] = ops.loop_membership(st['row'], st['col'],
                                              st['disp_index'], loop_pixels)
@@ -108,6 +110,8 @@ def prepare_chrom_sharded(csr, bias_raw, design, dist_min=4, dist_max=200,
         mean_thresh, dist_min)
     st.update(size_factors=sf, scaled=scaled, disp_idx=disp_idx,
               disp_index=ops.mask_to_index(disp_idx))
+    if table.dim() == 2:
+        st['sf_table'] = table
     if loop_pixels is not None:
         st['loop_idx'] = ops.loop_membership(st['row'], st['col'],
                                              st['disp_index'], loop_pixels)
@@ -170,22 +174,14 @@ def prepare_many(chrom_inputs, design, n_streams=None, sink=None, **kw):
     return [states[i] for i in sorted(states)]
 
 
-def pool_by_distance(states, dist_max, n_reps=None):
-    """Pools the disp_idx pixels of the given chromosomes by distance
-    (analysis/analysis.py:169-183, 196-197): returns (x, f) SoA (R, n) in
-    (distance key, chromosome, row, col) order, the per-pixel distances in
-    chromosome order, the segment boundaries over the keys (host int64) and
-    the per-chromosome offsets.  The key is the distance itself in a
-    one-process run and (owner rank, distance) otherwise
-    (hic3defdr_b200.dist.distance_keys)."""
+def _pool_local_order(states, dist_max):
+    """Distances of the tested pixels (chromosome order), their stable rank by
+    pooling key and the key boundaries: shared first half of both pooling
+    paths.  The key is the distance itself in a one-process run and (owner
+    rank, distance) otherwise (hic3defdr_b200.dist.distance_keys)."""
     counts = [int(s['disp_index'].numel()) for s in states]
     offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
     n_tot = int(offs[-1])
-    if n_reps is None:
-        # a rank without chromosomes must still take part in the exchange with
-        # the same number of replicate rows as the others: callers that may run
-        # multi-process pass the design's replicate count
-        n_reps = states[0]['raw'].shape[1] if states else 1
     dist_cat = torch.empty(n_tot, dtype=torch.int32, device='cuda')
     for s, o, n in zip(states, offs[:-1], counts):
         if s['size_factors'].dim() != 2:
@@ -196,25 +192,103 @@ def pool_by_distance(states, dist_max, n_reps=None):
             ops.gather_counts_factors(s['row'], s['col'], s['disp_index'],
                                       None, None, None, None, n_tot, None,
                                       None, dist_cat[o:o + n])
-    x = torch.empty((n_reps, max(n_tot, 1)), dtype=torch.float64,
-                    device='cuda')
-    f = torch.empty_like(x)
     key_of_dist, per = hdist.distance_keys(dist_max + 1)
     n_keys = per * hdist.world_size()
     if n_tot:
         keys = dist_cat if hdist.world_size() == 1 else \
             ops.dev(key_of_dist)[dist_cat.long()]
         rank, key_start = ops.stable_rank(keys, n_keys)
-        for s, o, n in zip(states, offs[:-1], counts):
-            if n:
-                ops.gather_counts_factors(
-                    s['row'], s['col'], s['disp_index'], s['raw'],
-                    s['size_factors'], s['bias'], rank[o:o + n], x.shape[1],
-                    x, f, None)
-        seg_start = ops.to_host(key_start)
     else:
-        seg_start = np.zeros(n_keys + 1, dtype=np.int64)
-    return x, f, dist_cat, seg_start, offs
+        rank = None
+        key_start = torch.zeros(n_keys + 1, dtype=torch.int64, device='cuda')
+    return counts, offs, dist_cat, rank, key_start, key_of_dist, per
+
+
+def _pool_gather(states, counts, offs, rank, key_start, key_of_dist, per,
+                 n_reps, owner_of_key, shift_of_key, bases, ld):
+    """The two pooling passes (csrc/peer.cu): records at the pooled
+    positions, then the coalesced gather into ``bases[owner]``."""
+    import ctypes
+    from hic3defdr_b200._native import lib, ptr
+    n_tot = int(offs[-1])
+    if not n_tot:
+        return
+    n_keys = len(owner_of_key)
+    rec = torch.empty((n_tot, 2), dtype=torch.int32, device='cuda')
+    table = np.zeros((len(states), 4), dtype=np.int64)
+    for ci, (s, o, n) in enumerate(zip(states, offs[:-1], counts)):
+        sf, mode = (s['sf_table'], 2) if 'sf_table' in s else \
+            (s['size_factors'], 1)
+        table[ci] = (s['raw'].data_ptr(), s['bias'].data_ptr(), sf.data_ptr(),
+                     mode)
+        if n:
+            lib().call('h3d_pool_index', ptr(s['row']), ptr(s['disp_index']),
+                       n, ci, ptr(rank[o:o + n]), ptr(rec), ops._stream())
+    dist_of_key = np.full(n_keys, -1, dtype=np.int32)
+    dist_of_key[key_of_dist] = np.arange(len(key_of_dist), dtype=np.int32)
+    peer_arr = (ctypes.c_void_p * len(bases))(*bases)
+    # named, so that the small tables stay allocated until the launch is queued
+    # (a temporary's block would be handed to the next temporary at once)
+    d_dist = ops.dev(dist_of_key)
+    d_owner = ops.dev(np.asarray(owner_of_key, dtype=np.int32))
+    d_shift = ops.dev(np.asarray(shift_of_key, dtype=np.int64))
+    d_table = ops.dev(table)
+    lib().call('h3d_pool_pull', ptr(rec), n_tot, ptr(key_start), n_keys,
+               ptr(d_dist), ptr(d_owner), ptr(d_shift), ptr(d_table),
+               len(states), n_reps, peer_arr, len(bases), int(ld),
+               ops._stream())
+
+
+def pool_by_distance(states, dist_max, n_reps=None):
+    """Pools the disp_idx pixels of the given chromosomes by distance
+    (analysis/analysis.py:169-183, 196-197) on this device: returns (x, f) SoA
+    (R, n) in (pooling key, chromosome, row, col) order -- the two halves of one
+    (2 R, n) buffer --, the per-pixel distances in chromosome order, the segment
+    boundaries over the keys (host int64) and the per-chromosome offsets."""
+    counts, offs, dist_cat, rank, key_start, key_of_dist, per = \
+        _pool_local_order(states, dist_max)
+    n_tot = int(offs[-1])
+    if n_reps is None:
+        # a rank without chromosomes must still take part in the exchange with
+        # the same number of replicate rows as the others: callers that may run
+        # multi-process pass the design's replicate count
+        n_reps = states[0]['raw'].shape[1] if states else 1
+    ld = max(n_tot, 1)
+    xf = torch.empty((2 * n_reps, ld), dtype=torch.float64, device='cuda')
+    n_keys = per * hdist.world_size()
+    _pool_gather(states, counts, offs, rank, key_start, key_of_dist, per,
+                 n_reps, np.zeros(n_keys, np.int32), np.zeros(n_keys, np.int64),
+                 [xf.data_ptr()], ld)
+    seg_start = ops.to_host(key_start)
+    return xf[:n_reps], xf[n_reps:], dist_cat, seg_start, offs
+
+
+def pool_to_owners(states, dist_max, n_reps):
+    """``pool_by_distance`` + the exchange by distance owner in one pass over
+    the pixels (multi-GPU, NCCL, one node): after the local stable rank by
+    (owner, distance) and ONE all-gather of the per-(rank, distance) counts,
+    the pooling gather writes every pixel's counts and factors straight into
+    the buffer of the rank that owns its distance, over NVLink (csrc/peer.cu).
+    Returns (x, f, dist_cat, runs, offs, n_owned) with x, f the two halves of
+    this rank's receive buffer."""
+    ws, me = hdist.world_size(), hdist.rank()
+    counts, offs, dist_cat, rank, key_start, key_of_dist, per = \
+        _pool_local_order(states, dist_max)
+    seg_start = ops.to_host(key_start)
+    # the collective also orders the ranks: nobody writes into a buffer whose
+    # previous contents are still being read (stream order on every rank)
+    all_counts = hdist._all_gather_counts(np.diff(seg_start))
+    n_recv, shift, runs = hdist.owner_layout(all_counts, per, me)
+    ld = (int(n_recv.max()) + 255) // 256 * 256 + 256
+    ptrs = hdist._PEERS.ensure(2 * n_reps * ld * 8)
+    owner_of_key = np.arange(per * ws) // per
+    _pool_gather(states, counts, offs, rank, key_start, key_of_dist, per,
+                 n_reps, owner_of_key, shift, ptrs, ld)
+    hdist.fence_peer_writes()
+    own = ptrs[me]
+    x = hdist.RawMatrix(own, (n_reps, ld))
+    f = hdist.RawMatrix(own + n_reps * ld * 8, (n_reps, ld))
+    return x, f, dist_cat, runs, offs, per
 
 
 _TREND_STREAMS = {}
@@ -269,23 +343,26 @@ def fit_trends(disp_per_dist, dist_max, cond_names, frac=None,
     return fns, table
 
 
-def _estimate_with_callable(x, f, seg_start, design, estimator):
+def _estimate_with_callable(x, f, runs, n_seg, design, estimator):
     """analysis/analysis.py:164-165, 186-206 with a user-supplied Python
     estimator ``(data (pixels, replicates), f=...) -> float``: the pooled
     pixels of every (distance, condition) bin are handed to it on the host, as
     the reference does; everything around it (pooling, exchange, trend, gather)
     stays on the device."""
     xs, fs = x.cpu().numpy(), f.cpu().numpy()
-    n_seg = len(seg_start) - 1
     out = np.full((n_seg, design.shape[1]), np.nan)
+    run_seg, run_lo, run_hi = runs
     for s in range(n_seg):
-        lo, hi = int(seg_start[s]), int(seg_start[s + 1])
-        if hi == lo:
+        cols = np.concatenate(
+            [np.arange(lo, hi) for g, lo, hi in zip(run_seg, run_lo, run_hi)
+             if g == s] + [np.zeros(0, dtype=np.int64)]).astype(np.int64)
+        if not len(cols):
             continue
         for c in range(design.shape[1]):
             reps = np.flatnonzero(design[:, c])
-            raw_slice = np.ascontiguousarray(xs[reps, lo:hi].T).astype(np.int64)
-            f_slice = np.ascontiguousarray(fs[reps, lo:hi].T)
+            raw_slice = np.ascontiguousarray(
+                xs[np.ix_(reps, cols)].T).astype(np.int64)
+            f_slice = np.ascontiguousarray(fs[np.ix_(reps, cols)].T)
             out[s, c] = estimator(raw_slice, f=f_slice)
     return out, dict(outer_iterations=0, nll_evaluations=0,
                      pixel_equalizations=0, launches=0, equalize_launches=0,
@@ -302,20 +379,29 @@ def estimate_disp(states, design, dist_max, cond_names=None, estimator='qcml',
     n_conds = design.shape[1]
     if cond_names is None:
         cond_names = [str(c) for c in range(n_conds)]
-    with stage('estimate_disp/pool'):
-        x, f, dist_cat, seg_start, offs = pool_by_distance(
-            states, dist_max, n_reps=design.shape[0])
-    n_tot = int(offs[-1])
-    # multi-GPU: every distance is estimated on the rank that owns it
-    with stage('estimate_disp/exchange'):
-        x, f, seg_start = hdist.exchange_by_distance(x, f, seg_start, n_tot)
+    if hdist.peer_exchange_enabled() and not callable(estimator):
+        # multi-GPU: the pooling gather writes into the owners' buffers
+        with stage('estimate_disp/pool'):
+            x, f, dist_cat, runs, offs, n_owned = pool_to_owners(
+                states, dist_max, design.shape[0])
+        n_tot = int(offs[-1])
+    else:
+        with stage('estimate_disp/pool'):
+            x, f, dist_cat, seg_start, offs = pool_by_distance(
+                states, dist_max, n_reps=design.shape[0])
+        n_tot = int(offs[-1])
+        # multi-GPU: every distance is estimated on the rank that owns it
+        n_keys = len(seg_start) - 1
+        with stage('estimate_disp/exchange'):
+            x, f, runs = hdist.exchange_by_distance(x, f, seg_start, n_tot)
+        n_owned = n_keys // hdist.world_size()
     with stage('estimate_disp/qcml'):
         if callable(estimator):
             disp_per_dist, stats = _estimate_with_callable(
-                x, f, seg_start, design, estimator)
+                x, f, runs, n_owned, design, estimator)
         else:
             disp_per_dist, stats = ops.estimate_dispersion(
-                x, f, seg_start, design, estimator)
+                x, f, n_owned, design, estimator, runs=runs)
     with stage('estimate_disp/merge'):
         disp_per_dist = hdist.merge_disp_per_dist(disp_per_dist, dist_max + 1)
     del x, f

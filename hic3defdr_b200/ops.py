@@ -439,25 +439,46 @@ def gather_counts_factors(row, col, index, raw, size_factors, bias, dest, ld,
                _stream())
 
 
-def estimate_dispersion(x_soa, f_soa, seg_start, design, estimator='qcml'):
+def estimate_dispersion(x_soa, f_soa, seg_start, design, estimator='qcml',
+                        runs=None):
     """Per-(segment, condition) dispersion of pooled SoA data.
-    x_soa, f_soa: (R, ld) CUDA; seg_start: host int64 (n_seg + 1).
+    x_soa, f_soa: (R, ld) CUDA; seg_start: host int64 (n_seg + 1) boundaries of
+    contiguous segments, or ``runs`` = (run_seg int32, run_lo int64, run_hi
+    int64) host arrays when a segment is a list of runs (include/h3d.h,
+    h3d_estimate_dispersion_runs; segment ids 0 .. max(run_seg)).
     Returns (disp (n_seg, C) numpy, stats dict)."""
     design = np.asarray(design).astype(bool)
     n_reps, n_conds = design.shape
-    seg = np.ascontiguousarray(seg_start, dtype=np.int64)
-    n_seg = len(seg) - 1
     ld = x_soa.shape[1]
-    out = np.empty((n_seg, n_conds))
     stats = np.zeros(9, dtype=np.int64)
-    wsb = lib().query('h3d_estimate_dispersion_ws_bytes', int(seg[-1]), n_seg,
-                      n_reps, n_conds)
-    ws = workspace(wsb)
     db = design_bytes(design)
-    lib().call('h3d_estimate_dispersion', ptr(x_soa), ptr(f_soa), ld,
-               ptr(seg), n_seg, ptr(db), n_reps, n_conds,
-               ESTIMATORS[estimator], ptr(out), ptr(stats), ptr(ws), wsb,
-               _stream())
+    if runs is None:
+        seg = np.ascontiguousarray(seg_start, dtype=np.int64)
+        n_seg = len(seg) - 1
+        out = np.empty((n_seg, n_conds))
+        wsb = lib().query('h3d_estimate_dispersion_ws_bytes', int(seg[-1]),
+                          n_seg, n_reps, n_conds)
+        ws = workspace(wsb)
+        lib().call('h3d_estimate_dispersion', ptr(x_soa), ptr(f_soa), ld,
+                   ptr(seg), n_seg, ptr(db), n_reps, n_conds,
+                   ESTIMATORS[estimator], ptr(out), ptr(stats), ptr(ws), wsb,
+                   _stream())
+    else:
+        run_seg = np.ascontiguousarray(runs[0], dtype=np.int32)
+        run_lo = np.ascontiguousarray(runs[1], dtype=np.int64)
+        run_hi = np.ascontiguousarray(runs[2], dtype=np.int64)
+        n_runs = len(run_seg)
+        n_seg = int(seg_start) if np.isscalar(seg_start) else \
+            (int(run_seg.max()) + 1 if n_runs else 1)
+        n_px = int((run_hi - run_lo).sum())
+        out = np.empty((n_seg, n_conds))
+        wsb = lib().query('h3d_estimate_dispersion_runs_ws_bytes', n_px,
+                          n_runs, n_seg, n_reps, n_conds)
+        ws = workspace(wsb)
+        lib().call('h3d_estimate_dispersion_runs', ptr(x_soa), ptr(f_soa), ld,
+                   ptr(run_seg), ptr(run_lo), ptr(run_hi), n_runs, n_seg,
+                   ptr(db), n_reps, n_conds, ESTIMATORS[estimator], ptr(out),
+                   ptr(stats), ptr(ws), wsb, _stream())
     if stats[8]:
         import sys
         print('  warning: the qCML fixed point of %d (distance, condition) bins '
@@ -664,7 +685,14 @@ def adjust_pvalues_ranked(pvalues, rank_offset, n_total):
 
 
 def apply_bh_carry(q, carry):
-    """q <- min(q, carry) in place, NaN kept (h3d_bh_apply_carry)."""
+    """q <- min(q, carry) in place, NaN kept; ``carry`` a float or a 0-dim
+    CUDA tensor (h3d_bh_apply_carry / h3d_bh_apply_carry_dev: the device form
+    needs no host round trip)."""
+    if isinstance(carry, torch.Tensor):
+        c = carry.to(torch.float64).contiguous().view(1)
+        lib().call('h3d_bh_apply_carry_dev', ptr(q), q.numel(), ptr(c),
+                   _stream())
+        return q
     lib().call('h3d_bh_apply_carry', ptr(q), q.numel(), float(carry),
                _stream())
     return q

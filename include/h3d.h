@@ -179,6 +179,43 @@ int h3d_gather_counts_factors(const int* row, const int* col, const int* index,
                               long long ld, double* x_out, double* f_out,
                               int* dist_out, h3d_stream_t stream);
 
+/* ---- multi-GPU pooling over peer memory ---------------------------------- */
+
+/* Receive buffers of the distance exchange (one process per GPU on one node):
+ * a cudaMalloc allocation plus the CUDA IPC handle the other ranks open.  The
+ * handle is H3D_PEER_HANDLE_BYTES opaque bytes, to be sent to the peers by any
+ * means (the host side uses torch.distributed). */
+#define H3D_PEER_HANDLE_BYTES 64
+int h3d_peer_alloc(size_t bytes, void** ptr_out, unsigned char* handle_out);
+int h3d_peer_free(void* ptr);
+int h3d_peer_open(const unsigned char* handle, void** ptr_out);
+int h3d_peer_close(void* ptr);
+
+/* Pooling by distance (hic3defdr/analysis/analysis.py:169-206: raw[dist == d],
+ * f[dist == d] genome-wide), two passes.
+ * Pass 1, per chromosome: tested pixel i (union index u = index[i]) drops the
+ * record {u, chrom_id << 24 | row[u]} (two int32) at rec[dest[i]], dest = its
+ * pooled position (stable rank by pooling key over all chromosomes).
+ * Pass 2, all chromosomes: pooled position p, of key k (key_start: device,
+ * n_keys + 1 boundaries; dist_of_key[k] = the distance), is gathered from the
+ * chromosome table (device, n_chroms rows of four 8-byte words: raw pointer,
+ * bias pointer, size-factor pointer, size-factor form 0: (R,), 1: (N, R),
+ * 2: (D + 1, R)) and written to column p + shift_of_key[k] of the (2 n_reps, ld)
+ * float64 matrix peer_base_host[owner_of_key[k]] (rows [0, R): counts, rows
+ * [R, 2R): factors f = bias[row] bias[col] size_factor).  One process:
+ * owner 0, shift 0, the matrix is the local pooled buffer.  Several processes:
+ * peer_base_host holds this rank's receive buffer and the opened peer buffers
+ * (HOST array of n_ranks device pointers), and the stores go over NVLink; the
+ * caller orders the ranks around the call (nobody reads a buffer before all
+ * writers are done, nobody writes before the previous contents are used up). */
+int h3d_pool_index(const int* row, const int* index, long long n_sel, int chrom_id,
+                   const int* dest, int* rec, h3d_stream_t stream);
+int h3d_pool_pull(const int* rec, long long n_local, const long long* key_start,
+                  int n_keys, const int* dist_of_key, const int* owner_of_key,
+                  const long long* shift_of_key, const void* chrom_table,
+                  int n_chroms, int n_reps, void* const* peer_base_host,
+                  int n_ranks, long long ld, h3d_stream_t stream);
+
 /* Stable rank of every element when sorting by an integer key in
  * [0, n_keys): rank_out[i] = position of element i; key_start: (n_keys + 1)
  * int64 group boundaries.  Used for equal_bin (util/binning.py:25) and for
@@ -219,6 +256,23 @@ int h3d_estimate_dispersion(const double* x, const double* f, long long ld,
                             void* ws, size_t ws_bytes, h3d_stream_t stream);
 size_t h3d_estimate_dispersion_ws_bytes(long long n_px, int n_seg, int n_reps,
                                         int n_conds);
+
+/* The same with every segment given as a LIST OF RUNS of the pooled arrays:
+ * run r = pixels [run_lo_host[r], run_hi_host[r]) of segment run_seg_host[r].
+ * After the multi-GPU exchange of hic3defdr/analysis/analysis.py:169-206's
+ * pooling, a distance's pixels arrive as one run per source rank; the
+ * likelihood sums are exact (order independent), so the runs are consumed where
+ * they land instead of being regrouped into contiguous segments. */
+int h3d_estimate_dispersion_runs(const double* x, const double* f, long long ld,
+                                 const int* run_seg_host,
+                                 const long long* run_lo_host,
+                                 const long long* run_hi_host, int n_runs,
+                                 int n_seg, const unsigned char* design_host,
+                                 int n_reps, int n_conds, int estimator,
+                                 double* disp_per_dist_host, long long* stats_host,
+                                 void* ws, size_t ws_bytes, h3d_stream_t stream);
+size_t h3d_estimate_dispersion_runs_ws_bytes(long long n_px, int n_runs, int n_seg,
+                                             int n_reps, int n_conds);
 
 /* equalize, hic3defdr/util/scaled_nb.py:186-214 (with q2qnbinom, :217-275):
  * pseudo-data of ONE bin at dispersion ``alpha``.  x, f: SoA (n_reps, ld),
@@ -312,6 +366,9 @@ int h3d_bh_ranked(const double* p, long long n, long long rank_offset, long long
                   double* q, double* min_out, void* ws, size_t ws_bytes,
                   h3d_stream_t stream);
 int h3d_bh_apply_carry(double* q, long long n, double carry, h3d_stream_t stream);
+/* the same with the carry read from device memory (no host round trip) */
+int h3d_bh_apply_carry_dev(double* q, long long n, const double* carry_dev,
+                           h3d_stream_t stream);
 
 /* ---- threshold / classify (the step after bh) ------------------------------ */
 

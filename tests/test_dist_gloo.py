@@ -48,20 +48,48 @@ def _worker(rank, world, port, ret):
         x = np.stack([dist * 1000.0 + rank * 100 + r for r in range(n_reps)])
         ident = rng.random(n)                       # per-pixel tag
         f = np.stack([ident + r for r in range(n_reps)])
-        xo, fo, seg_o = hd.exchange_by_distance(
+        xo, fo, runs = hd.exchange_by_distance(
             torch.from_numpy(x), torch.from_numpy(f), seg, n)
         mine_d = hd.owned_distances(n_dist)
-        assert len(seg_o) == per + 1
-        n_got = int(seg_o[-1])
+        run_seg, run_lo, run_hi = runs
+        assert len(run_seg) == per * world
+        assert (np.diff(run_seg) >= 0).all()        # by owned key, then source
+        n_got = int((run_hi - run_lo).sum())
         xo, fo = xo.numpy()[:, :n_got], fo.numpy()[:, :n_got]
+        seg_o = np.concatenate([[0], np.cumsum(np.bincount(
+            run_seg, weights=run_hi - run_lo, minlength=per))]).astype(int)
+        covered = np.zeros(n_got, dtype=int)
         for j in range(per):
-            a, b = int(seg_o[j]), int(seg_o[j + 1])
-            if j >= len(mine_d):
-                assert a == b
-                continue
-            assert (xo[0, a:b] // 1000 == mine_d[j]).all()
-            src = (xo[0, a:b] % 1000) // 100
-            assert (np.diff(src) >= 0).all()        # rank order inside a distance
+            last_src = -1
+            for g, a, b in zip(run_seg, run_lo, run_hi):
+                if g != j or a == b:
+                    continue
+                assert j < len(mine_d)
+                covered[a:b] += 1
+                assert (xo[0, a:b] // 1000 == mine_d[j]).all()
+                src = (xo[0, a:b] % 1000) // 100
+                assert len(set(src.tolist())) == 1 and src[0] > last_src
+                last_src = src[0]                   # one run per source, in rank order
+        assert (covered == 1).all()
+        # the peer-memory exchange (csrc/peer.cu) derives the same layout from
+        # the all-gathered counts alone: identical runs, and every local pixel
+        # lands inside its run of the owner's buffer
+        allc = hd._all_gather_counts(np.diff(seg))
+        n_recv, shift, runs2 = hd.owner_layout(allc, per, rank)
+        for a, b in zip(runs, runs2):
+            assert np.array_equal(a, b)
+        assert int(n_recv[rank]) == n_got
+        layouts = [None] * world
+        td.all_gather_object(layouts, (shift.tolist(), seg.tolist()))
+        for src, (sh, sg) in enumerate(layouts):
+            for key in range(per * world):
+                if key // per != rank or sg[key + 1] == sg[key]:
+                    continue
+                j = key - rank * per
+                sel = [(a, b) for g, a, b in zip(*runs2) if g == j]
+                lo_run, hi_run = sel[src]           # one run per source, in order
+                assert sg[key] + sh[key] == lo_run
+                assert sg[key + 1] + sh[key] == hi_run
         # every pixel arrived exactly once, on exactly one rank
         tags = [None] * world
         td.all_gather_object(tags, fo[0].tolist())
@@ -106,7 +134,7 @@ def _worker(rank, world, port, ret):
             torch.from_numpy(p_local),
             bh_fn=lambda t: torch.from_numpy(op.bh(t.numpy())),
             bh_ranked_fn=ranked,
-            carry_fn=lambda q, c: torch.where(q > c, torch.full_like(q, c), q))
+            carry_fn=lambda q, c: torch.where(q > c, c.to(q.dtype).expand_as(q), q))
         allp = [None] * world
         td.all_gather_object(allp, p_local.tolist())
         q_all = op.bh(np.concatenate([np.array(v) for v in allp]))
