@@ -48,6 +48,7 @@ SIGNATURES = {
     'h3d_peer_free': (c_int, [vp]),
     'h3d_peer_open': (c_int, [vp, vp]),
     'h3d_peer_close': (c_int, [vp]),
+    'h3d_peer_copy': (c_int, [vp, vp, vp, vp, vp, c_int, vp]),
     'h3d_pool_index': (c_int, [vp, vp, c_ll, c_int, vp, vp, vp]),
     'h3d_pool_pull': (c_int, [vp, c_ll, vp, c_int, vp, vp, vp, vp, c_int, c_int,
                               vp, c_int, c_ll, vp]),
@@ -82,6 +83,17 @@ SIGNATURES = {
     'h3d_bh_ranked': (c_int, [vp, c_ll, c_ll, c_ll, vp, vp, vp, c_sz, vp]),
     'h3d_bh_apply_carry': (c_int, [vp, c_ll, c_dbl, vp]),
     'h3d_bh_apply_carry_dev': (c_int, [vp, c_ll, vp, vp]),
+    'h3d_roc_sort': (c_int, [vp, vp, c_ll, vp, vp, vp, vp, c_sz, vp]),
+    'h3d_roc_sort_ws_bytes': (c_sz, [c_ll]),
+    'h3d_roc_points': (c_int, [vp, vp, c_ll, vp, c_ll, vp, vp, vp, vp, vp]),
+    'h3d_nb_simulate': (c_int, [vp, vp, vp, c_ll, vp, c_int, vp, c_int, c_int,
+                                vp, c_int, c_int, ctypes.c_ulonglong, vp, vp,
+                                vp]),
+    'h3d_perturb': (c_int, [vp, c_ll, vp, vp, c_ll, vp, vp]),
+    'h3d_kr_balance': (c_int, [vp, vp, vp, c_int, c_dbl, vp, c_dbl, c_dbl,
+                               c_int, vp, vp, c_int, vp, vp, vp, c_sz, vp]),
+    'h3d_kr_balance_ws_bytes': (c_sz, [c_int]),
+    'h3d_band_nnz': (c_int, [vp, vp, vp, c_int, c_int, vp, vp, vp]),
     'h3d_connected_components': (c_int, [vp, vp, c_ll, vp, vp, vp, c_sz, vp]),
     'h3d_connected_components_ws_bytes': (c_sz, [c_ll]),
 }

@@ -685,6 +685,124 @@ class HiC3DeFDR(object):
                         found, '%s/%s_%g_%i_%s.json'
                         % (self.outdir, cond, f, s, chrom), chrom)
 
+    # -------------------------------------------------------------- simulate
+    def simulate(self, cond, chrom=None, beta=0.5, p_diff=0.4, skip_bias=False,
+                 loop_pattern=None, outdir='sim', n_threads=-1, verbose=True):
+        """analysis/simulation.py:22-144: simulates raw contact matrices from
+        the fitted scaled means and the dispersion trend of condition ``cond``,
+        perturbing the loops of ``loop_pattern``; writes
+        ``<outdir>/<rep>_<chrom>_raw.npz``, ``labels_<chrom>.txt`` and
+        ``design.csv``.  The sampling runs on the GPU (csrc/simulate.cu)."""
+        from hic3defdr_b200 import simulation as hsim
+        if chrom is None:
+            for c in self._cluster_chroms():
+                self.simulate(cond, chrom=c, beta=beta, p_diff=p_diff,
+                              skip_bias=skip_bias, loop_pattern=loop_pattern,
+                              outdir=outdir, verbose=False)
+            hdist.barrier()
+            return
+        eprint('simulating data for chrom %s' % chrom)
+        if loop_pattern is None:
+            loop_pattern = self.loop_patterns[cond]
+        sel = np.asarray(self.design[cond].values).astype(bool)
+        bias = self.load_bias(chrom)[:, sel]
+        size_factors = self.load_data('size_factors', chrom)
+        size_factors = size_factors[:, sel] if size_factors.ndim == 2 \
+            else size_factors[sel]
+        row = self.load_data('row', chrom)
+        col = self.load_data('col', chrom)
+        scaled = self.load_data('scaled', chrom)[:, sel]
+        disp_fn = self.load_disp_fn(cond)
+        clusters = load_clusters(loop_pattern.replace('<chrom>', chrom))
+        mean = np.mean(scaled, axis=1)
+        os.makedirs(outdir, exist_ok=True)
+        n_sim_per_cond = size_factors.shape[-1]
+        repnames = sum((['%s%i' % (c, i + 1) for i in range(n_sim_per_cond)]
+                        for c in ['A', 'B']), [])
+        design_file = '%s/design.csv' % outdir
+        if not os.path.isfile(design_file):
+            pd.DataFrame(
+                {'A': [1] * n_sim_per_cond + [0] * n_sim_per_cond,
+                 'B': [0] * n_sim_per_cond + [1] * n_sim_per_cond},
+                dtype=bool, index=repnames).to_csv(design_file)
+        if size_factors.ndim == 2:
+            # one row per distance (the first pixel at that distance)
+            eprint('  converting size factors', skip=not verbose)
+            dist = col - row
+            n_dists = int(dist.max()) + 1
+            first = np.full(n_dists, 0, dtype=np.int64)
+            seen = np.zeros(n_dists, dtype=bool)
+            idx = np.arange(len(dist))[::-1]
+            first[dist[::-1]] = idx
+            seen[dist] = True
+            table = size_factors[first, :]
+            table[~seen] = size_factors[0, :]    # np.argmax of an all-False mask
+            size_factors = table
+        if skip_bias:
+            bias = np.ones_like(bias)
+            size_factors = np.ones_like(size_factors)
+        bias = np.tile(bias, 2)
+        size_factors = np.tile(size_factors, 2)
+        classes, sim_iter = hsim.simulate(
+            row, col, mean, disp_fn, bias, size_factors, clusters, beta=beta,
+            p_diff=p_diff, trend='dist', verbose=verbose)
+        np.savetxt('%s/labels_%s.txt' % (outdir, chrom), classes, fmt='%s')
+        for rep, csr in zip(repnames, sim_iter):
+            sparse.save_npz('%s/%s_%s_raw.npz' % (outdir, rep, chrom), csr)
+
+    # -------------------------------------------------------------- evaluate
+    def evaluate(self, cluster_pattern, label_pattern, min_dist=None,
+                 max_dist=None, rerun_bh=False, outfile=None):
+        """analysis/simulation.py:146-239: ROC / FDR-control curves of the
+        q-values against the ground-truth labels of a simulation; writes
+        ``<outdir>/eval.npz`` (or ``eval_<min_dist>_<max_dist>.npz``) with
+        ``fdr``, ``fpr``, ``tpr``, ``thresh``.  Runs on rank 0."""
+        from hic3defdr_b200 import evaluation as hev
+        if outfile is None:
+            outfile = 'eval.npz' if min_dist is None and max_dist is None \
+                else 'eval_%s_%s.npz' % (min_dist, max_dist)
+        if self.loop_patterns and cluster_pattern in self.loop_patterns.keys():
+            cluster_pattern = self.loop_patterns[cluster_pattern]
+        if hdist.rank() == 0:
+            y_true, pvalues, qvalues = [], [], []
+            for chrom in self.chroms:
+                disp_idx = self.load_data('disp_idx', chrom)
+                loop_idx = self.load_data('loop_idx', chrom)
+                row = self.load_data('row', chrom, idx=(disp_idx, loop_idx))
+                col = self.load_data('col', chrom, idx=(disp_idx, loop_idx))
+                clusters = load_clusters(
+                    cluster_pattern.replace('<chrom>', chrom))
+                labels = np.loadtxt(label_pattern.replace('<chrom>', chrom),
+                                    dtype='U7')
+                dist = col - row
+                dist_idx = np.ones(len(dist), dtype=bool)
+                if min_dist is not None:
+                    dist_idx[dist < min_dist] = False
+                if max_dist is not None:
+                    dist_idx[dist > max_dist] = False
+                y_true.append(hev.make_y_true(row[dist_idx], col[dist_idx],
+                                              clusters, labels))
+                if min_dist is not None or max_dist is not None:
+                    if rerun_bh:
+                        pvalues.append(self.load_data(
+                            'pvalues', chrom, idx=(loop_idx, dist_idx)))
+                    else:
+                        qvalues.append(self.load_data('qvalues', chrom,
+                                                      idx=dist_idx))
+            y_true = np.concatenate(y_true)
+            if pvalues:
+                with hdist.single_process():
+                    qvalues = ops.adjust_pvalues(
+                        np.concatenate(pvalues)).cpu().numpy()
+            elif qvalues:
+                qvalues = np.concatenate(qvalues)
+            else:
+                qvalues, _ = self.load_data('qvalues', 'all')
+            fdr, fpr, tpr, thresh = hev.evaluate(y_true, qvalues)
+            np.savez('%s/%s' % (self.outdir, outfile),
+                     **{'fdr': fdr, 'fpr': fpr, 'tpr': tpr, 'thresh': thresh})
+        hdist.barrier()
+
     def collect(self, fdr=0.05, cluster_size=3, n_threads=-1):
         """analysis/analysis.py:498-574: one ``results_<fdr>_<size>.tsv`` with
         the constitutive (insig) and per-condition clusters of every

@@ -77,6 +77,26 @@ pool_pull_kernel(const int2* __restrict__ rec, long long n_local,
     }
 }
 
+// contiguous slices from local memory into (peer) buffers, 8-byte words,
+// consecutive threads -> consecutive addresses (full-width NVLink stores)
+constexpr int kMaxSlices = 16;
+struct CopySlices {
+    const unsigned long long* src[kMaxSlices];
+    unsigned long long* dst[kMaxSlices];
+    long long words[kMaxSlices];
+};
+
+__global__ void __launch_bounds__(256)
+peer_copy_kernel(CopySlices sl) {
+    const int k = blockIdx.y;
+    const unsigned long long* __restrict__ src = sl.src[k];
+    unsigned long long* __restrict__ dst = sl.dst[k];
+    const long long n = sl.words[k];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        dst[i] = src[i];
+}
+
 }  // namespace h3d
 
 using namespace h3d;
@@ -142,5 +162,30 @@ extern "C" int h3d_pool_pull(const int* rec, long long n_local, const long long*
         (const int2*)rec, n_local, key_start, n_keys, dist_of_key, owner_of_key, shift_of_key,
         (const ChromSrc*)chrom_table, n_reps, pb, ld);
     H3D_LAUNCHED("pool_pull_kernel");
+    return H3D_OK;
+}
+
+extern "C" int h3d_peer_copy(const void* src_base, const long long* src_off_host,
+                             void* const* dst_base_host, const long long* dst_off_host,
+                             const long long* bytes_host, int n_slices, h3d_stream_t stream) {
+    H3D_REQUIRE(n_slices >= 0 && n_slices <= kMaxSlices, "at most 16 slices per call");
+    CopySlices sl;
+    long long longest = 0;
+    for (int k = 0; k < kMaxSlices; ++k) {
+        sl.src[k] = nullptr; sl.dst[k] = nullptr; sl.words[k] = 0;
+        if (k >= n_slices) continue;
+        H3D_REQUIRE(src_off_host[k] % 8 == 0 && dst_off_host[k] % 8 == 0 && bytes_host[k] % 8 == 0 &&
+                    bytes_host[k] >= 0, "slices are multiples of 8 bytes");
+        sl.src[k] = (const unsigned long long*)((const char*)src_base + src_off_host[k]);
+        sl.dst[k] = (unsigned long long*)((char*)dst_base_host[k] + dst_off_host[k]);
+        sl.words[k] = bytes_host[k] / 8;
+        if (sl.words[k] > longest) longest = sl.words[k];
+    }
+    if (n_slices == 0 || longest == 0) return H3D_OK;
+    int gx = div_up(longest, 256 * 8);
+    const int cap = kNumSMs * 8 / n_slices + 1;
+    if (gx > cap) gx = cap;
+    peer_copy_kernel<<<dim3(gx, n_slices), 256, 0, (cudaStream_t)stream>>>(sl);
+    H3D_LAUNCHED("peer_copy_kernel");
     return H3D_OK;
 }

@@ -154,24 +154,37 @@ def regroup_positions(recv_counts, device):
     return pos
 
 
+def distance_owner(n_dist, n_ranks=None):
+    """Owner rank of every distance.  Distances are dealt in boustrophedon
+    order (0 .. G-1, G-1 .. 0, 0 .. G-1, ...): the cost of a (distance,
+    condition) bin falls smoothly with the distance (fewer pixels, fewer counts
+    per pixel, shorter incomplete-gamma loops), so plain round robin hands rank
+    0 the more expensive member of every group of G (equalize 11 % above the
+    mean at G = 8); reversing every other group cancels the trend to first
+    order."""
+    ws = world_size() if n_ranks is None else n_ranks
+    d = np.arange(n_dist)
+    grp, pos = d // ws, d % ws
+    return np.where(grp % 2 == 0, pos, ws - 1 - pos).astype(np.int64)
+
+
 def distance_keys(n_dist, n_ranks=None):
-    """Pooling key of every distance: distances are dealt to ranks round robin
-    (owner(d) = d mod n_ranks -- the cost of a (distance, condition) bin varies
-    smoothly with d, so interleaving balances pixels AND qCML iterations), and
-    the key orders a rank's pooled pixels by (owner, distance):
-    key(d) = owner(d) * per + d // n_ranks, per = ceil(n_dist / n_ranks).
-    Returns (key per distance int32, per).  Identity for one process."""
+    """Pooling key of every distance: the key orders a rank's pooled pixels by
+    (owner, distance): key(d) = owner(d) * per + d // n_ranks,
+    per = ceil(n_dist / n_ranks) (every rank owns one distance of every group
+    of n_ranks consecutive ones, ``distance_owner``).  Returns (key per
+    distance int32, per).  Identity for one process."""
     ws = world_size() if n_ranks is None else n_ranks
     per = -(-n_dist // ws)
     d = np.arange(n_dist)
-    return ((d % ws) * per + d // ws).astype(np.int32), per
+    return (distance_owner(n_dist, ws) * per + d // ws).astype(np.int32), per
 
 
 def owned_distances(n_dist, me=None, n_ranks=None):
     """distances owned by rank ``me``, in key order"""
     ws = world_size() if n_ranks is None else n_ranks
     me = rank() if me is None else me
-    return np.arange(me, n_dist, ws)
+    return np.flatnonzero(distance_owner(n_dist, ws) == me)
 
 
 def exchange_by_distance(x, f, seg_start, n_local):
@@ -327,7 +340,38 @@ class PeerBuffers(object):
         self.nbytes, self.own, self.ptrs = 0, None, None
 
 
-_PEERS = PeerBuffers()
+_PEERS = PeerBuffers()            # dispersion pooling
+_BH_PEERS = PeerBuffers()         # p-values out, q-values back
+
+
+class _CudaArray(object):
+    def __init__(self, address, n, typestr):
+        self.__cuda_array_interface__ = dict(
+            shape=(int(n),), typestr=typestr, data=(int(address), False),
+            version=2)
+
+
+def _raw_tensor(address, n, dtype):
+    """zero-copy 1-D torch view of device memory torch did not allocate"""
+    if n == 0:
+        return torch.empty(0, dtype=dtype, device='cuda')
+    assert dtype == torch.float64
+    return torch.as_tensor(_CudaArray(address, n, '<f8'), device='cuda')
+
+
+def _peer_copy(src, src_off, ptrs, dst_off, nbytes):
+    """slice k of ``src`` (byte offsets) into rank k's buffer"""
+    import ctypes
+    from hic3defdr_b200._native import lib, ptr
+    ws = len(ptrs)
+    for k0 in range(0, ws, 16):
+        k1 = min(ws, k0 + 16)
+        so = np.ascontiguousarray(src_off[k0:k1], dtype=np.int64)
+        do = np.ascontiguousarray(dst_off[k0:k1], dtype=np.int64)
+        nb = np.ascontiguousarray(nbytes[k0:k1], dtype=np.int64)
+        bases = (ctypes.c_void_p * (k1 - k0))(*ptrs[k0:k1])
+        lib().call('h3d_peer_copy', ptr(src), ptr(so), bases, ptr(do),
+                   ptr(nb), k1 - k0, torch.cuda.current_stream().cuda_stream)
 
 
 def peer_exchange_enabled():
@@ -425,21 +469,18 @@ def global_bh(local_p, bh_fn=None, bh_ranked_fn=None, carry_fn=None):
     n = local_p.numel()
     device = local_p.device
     finite = torch.isfinite(local_p)
-    # splitters: evenly strided local sample of the finite values (a stable
-    # partition brings them to the front; no host round trip for their count)
-    fpos, fsizes = _partition((~finite).to(torch.int32), 2)
-    n_fin_t = fsizes[0]
+    n_fin_t = finite.sum()
+    # splitters: an evenly strided local sample (non-finite entries count as
+    # +inf and fall out below; the sample only decides the balance of the
+    # buckets, never the result)
     sample = torch.full((BH_SAMPLES,), float('inf'), dtype=local_p.dtype,
                         device=device)
     if n:
-        fin_first = torch.empty_like(local_p)
-        fin_first[fpos] = local_p
-        k = torch.arange(BH_SAMPLES, dtype=torch.int64, device=device)
-        take = torch.clamp(n_fin_t, max=BH_SAMPLES)
-        sel = (k * torch.clamp(n_fin_t - 1, min=0)) // \
-            torch.clamp(take - 1, min=1)
-        vals = fin_first[torch.clamp(sel, max=max(n - 1, 0))]
-        sample = torch.where(k < take, vals, sample)
+        take = min(BH_SAMPLES, n)
+        sel = sample_positions(n, take, device)
+        vals = local_p[sel]
+        sample[:take] = torch.where(torch.isfinite(vals), vals,
+                                    torch.full_like(vals, float('inf')))
     gathered = _all_gather_flat(sample)
     allsamp = torch.sort(gathered.view(-1)).values
     n_samp = torch.isfinite(allsamp).sum()
@@ -458,9 +499,24 @@ def global_bh(local_p, bh_fn=None, bh_ranked_fn=None, carry_fn=None):
     counts, n_total = table[:, :ws], int(table[:, ws].sum())
     send_splits = [int(v) for v in counts[me]]
     recv_splits = [int(v) for v in counts[:, me]]
-    recv = torch.empty(sum(recv_splits), dtype=local_p.dtype, device=device)
-    td.all_to_all_single(recv, send, output_split_sizes=recv_splits,
-                         input_split_sizes=send_splits)
+    peer = local_p.is_cuda and peer_exchange_enabled()
+    if peer:
+        # both all-to-alls as direct stores into the peers' buffers (NVLink,
+        # csrc/peer.cu): region A receives the p-values of this rank's value
+        # range, region B the q-values of this rank's own pixels
+        cap_a = int(counts.sum(axis=0).max())
+        cap_b = int(counts.sum(axis=1).max())
+        ptrs = _BH_PEERS.ensure((cap_a + cap_b) * 8)
+        src_off = np.concatenate([[0], np.cumsum(counts[me])[:-1]]) * 8
+        dst_off = counts[:me].sum(axis=0) * 8            # my slot in owner k's region A
+        _peer_copy(send, src_off, ptrs, dst_off, counts[me] * 8)
+        fence_peer_writes()
+        recv = _raw_tensor(ptrs[me], sum(recv_splits), local_p.dtype)
+    else:
+        recv = torch.empty(sum(recv_splits), dtype=local_p.dtype,
+                           device=device)
+        td.all_to_all_single(recv, send, output_split_sizes=recv_splits,
+                             input_split_sizes=send_splits)
     # non-finite values sit in the last bucket only, so the sizes of the
     # lower buckets are counts of finite values
     rank_offset = int(counts[:, :me].sum())
@@ -469,10 +525,18 @@ def global_bh(local_p, bh_fn=None, bh_ranked_fn=None, carry_fn=None):
     inf = torch.full((1,), float('inf'), dtype=mins.dtype, device=mins.device)
     carry = torch.cat([mins[me + 1:], inf]).min()       # stays on the device
     q_bucket = carry_fn(q_bucket, carry)
-    back = torch.empty_like(send)
-    td.all_to_all_single(back, q_bucket, output_split_sizes=send_splits,
-                         input_split_sizes=recv_splits)
-    return back[pos] if n else back
+    if peer:
+        src_off = np.concatenate([[0], np.cumsum(counts[:, me])[:-1]]) * 8
+        # bucket ``me`` of source s starts after its lower buckets in s's order
+        dst_off = (cap_a + counts[:, :me].sum(axis=1)) * 8
+        _peer_copy(q_bucket, src_off, ptrs, dst_off, counts[:, me] * 8)
+        fence_peer_writes()
+        back = _raw_tensor(ptrs[me] + cap_a * 8, n, local_p.dtype)
+    else:
+        back = torch.empty_like(send)
+        td.all_to_all_single(back, q_bucket, output_split_sizes=send_splits,
+                             input_split_sizes=recv_splits)
+    return back[pos] if n else torch.empty_like(send)
 
 
 def _coll_tensor(a, like=None):

@@ -416,7 +416,7 @@ def loop_membership(row, col, index, pixels):
     keys = np.array(sorted({(int(i) << 32) | int(j) for i, j in pixels}),
                     dtype=np.int64)
     kd = dev(keys)
-    n = index.numel()
+    n = index.numel() if index is not None else row.numel()
     out = torch.empty(n, dtype=torch.uint8, device='cuda')
     lib().call('h3d_loop_membership', ptr(row), ptr(col), ptr(index), n,
                ptr(kd), kd.numel(), ptr(out), _stream())

@@ -48,14 +48,17 @@ def band_coords(n, width):
 
 
 def make_chrom(n, n_reps, dist_max, seed, amp=300.0, res_scale=1.0, pad=5,
-               loops=False, bad_frac=0.01, dtype=np.int64):
-    """Returns (list of CSR matrices, bias array (n, n_reps), loop clusters)."""
+               loops=False, bad_frac=0.01, dtype=np.int64,
+               return_classes=False):
+    """Returns (list of CSR matrices, bias array (n, n_reps), loop clusters
+    [, ground-truth class of every cluster: 'constit', 'A' or 'B'])."""
     row, col = band_coords(n, dist_max + pad)
     d = (col - row).astype(float)
     mu = amp / (1.0 + d)
     phi = 0.01 + 1e-4 * d * res_scale
     clusters = None
     effect = None
+    classes = None
     if loops:
         lrng = np.random.default_rng(seed + 77)
         effect = np.ones((2, len(row)))
@@ -66,6 +69,7 @@ def make_chrom(n, n_reps, dist_max, seed, amp=300.0, res_scale=1.0, pad=5,
         li = lrng.integers(2, max(3, n - dist_max - 3), size=n_loops)
         ld = lrng.integers(10, min(150, dist_max - 2) + 1, size=n_loops)
         cls = lrng.choice(3, size=n_loops, p=[0.6, 0.2, 0.2])
+        classes = np.array(['constit', 'A', 'B'], dtype='U7')[cls]
         key = row * (dist_max + pad + 1) + (col - row)
         order = np.argsort(key)
         skey = key[order]
@@ -101,6 +105,8 @@ def make_chrom(n, n_reps, dist_max, seed, amp=300.0, res_scale=1.0, pad=5,
         nz = x > 0
         mats.append(sparse.csr_matrix(
             (x[nz].astype(dtype), (row[nz], col[nz])), shape=(n, n)))
+    if return_classes:
+        return mats, bias, clusters, classes
     return mats, bias, clusters
 
 
@@ -116,9 +122,9 @@ def write_dataset(root, chrom_sizes, n_reps=4, dist_max=200, config=1,
     loop_patterns = None
     for ci, (chrom, n) in enumerate(chrom_sizes.items()):
         seed = BASE_SEED + 1000 * config + 100 * ci
-        mats, bias, clusters = make_chrom(
+        mats, bias, clusters, classes = make_chrom(
             n, n_reps, dist_max, seed, amp=amp, res_scale=res_scale,
-            loops=loops, dtype=dtype)
+            loops=loops, dtype=dtype, return_classes=True)
         for r, rep in enumerate(rep_names):
             sparse.save_npz(os.path.join(root, rep, '%s_raw.npz' % chrom),
                             mats[r])
@@ -130,6 +136,10 @@ def write_dataset(root, chrom_sizes, n_reps=4, dist_max=200, config=1,
             with open(os.path.join(root, 'clusters', 'loops_%s.json' % chrom),
                       'w') as h:
                 json.dump([[list(p) for p in c] for c in clusters], h)
+            # ground truth in the format of the reference's simulate()
+            # (analysis/simulation.py:141: one label per cluster)
+            np.savetxt(os.path.join(root, 'clusters', 'labels_%s.txt' % chrom),
+                       classes, fmt='%s')
             loop_patterns = {
                 'A': os.path.join(root, 'clusters', 'loops_<chrom>.json'),
                 'B': os.path.join(root, 'clusters', 'loops_<chrom>.json')}

@@ -191,6 +191,16 @@ int h3d_peer_free(void* ptr);
 int h3d_peer_open(const unsigned char* handle, void** ptr_out);
 int h3d_peer_close(void* ptr);
 
+/* n_slices (<= 16) contiguous slices of local device memory into (peer)
+ * buffers: slice k = bytes_host[k] bytes from src_base + src_off_host[k] to
+ * dst_base_host[k] + dst_off_host[k] (all multiples of 8).  The all-to-all of
+ * the distributed BH correction (analysis/analysis.py:296-303 is global):
+ * every rank stores its partition of the p-values directly into the owners'
+ * receive buffers, and the q-values come back the same way. */
+int h3d_peer_copy(const void* src_base, const long long* src_off_host,
+                  void* const* dst_base_host, const long long* dst_off_host,
+                  const long long* bytes_host, int n_slices, h3d_stream_t stream);
+
 /* Pooling by distance (hic3defdr/analysis/analysis.py:169-206: raw[dist == d],
  * f[dist == d] genome-wide), two passes.
  * Pass 1, per chromosome: tested pixel i (union index u = index[i]) drops the
@@ -381,6 +391,69 @@ int h3d_bh_apply_carry_dev(double* q, long long n, const double* carry_dev,
 int h3d_connected_components(const int* row, const int* col, long long n, int* label,
                              int* size, void* ws, size_t ws_bytes, h3d_stream_t stream);
 size_t h3d_connected_components_ws_bytes(long long n);
+
+/* ---- evaluate (ROC / FDR curves) ----------------------------------------- */
+
+/* sklearn.metrics.roc_curve as used by hic3defdr/util/evaluation.py:44-79
+ * (evaluate; called from analysis/simulation.py:146-239), in two calls.
+ * h3d_roc_sort: scores 1 - q sorted descending; keys_sorted (n uint64,
+ * order-preserving image of the scores), boundary[i] = 1 at the last element
+ * of every run of equal scores, y_sorted = the labels in that order.
+ * h3d_roc_points: for the thresholds at sorted positions thr_idx (the set
+ * entries of boundary, m of them) and the sorted positions pos_idx of the
+ * n_pos positives: tps, fps (int64), thresholds (the scores), and keep[t] = 1
+ * for the points sklearn's drop_intermediate retains. */
+int h3d_roc_sort(const double* qvalues, const unsigned char* y_true, long long n,
+                 unsigned long long* keys_sorted, unsigned char* boundary,
+                 unsigned char* y_sorted, void* ws, size_t ws_bytes,
+                 h3d_stream_t stream);
+size_t h3d_roc_sort_ws_bytes(long long n);
+int h3d_roc_points(const unsigned long long* keys_sorted, const int* thr_idx,
+                   long long m, const int* pos_idx, long long n_pos, long long* tps,
+                   long long* fps, double* thresholds, unsigned char* keep,
+                   h3d_stream_t stream);
+
+/* ---- simulate / balance -------------------------------------------------- */
+
+/* One simulated replicate, hic3defdr/util/simulation.py:177-202: for pixel i,
+ * f = bias[row, rep] bias[col, rep] size_factor (size_factors: (n_sim,), or
+ * (n_dist, n_sim) by distance when sf_by_distance), bm = mean[i] f, count ~
+ * NB(mean bm, variance bm + disp bm^2) with disp = disp[col - row] (a
+ * (n_dist,) table; trend 'dist') or disp[i] (disp_per_pixel; trend 'mean').
+ * bias: (n_bins, n_sim) row-major.  counts_out: int64 (n,); biased_mean_out:
+ * optional (n,).  The stream of pixel i, replicate rep is Philox4x32-10 keyed
+ * by ``seed``: results do not depend on the launch geometry. */
+int h3d_nb_simulate(const int* row, const int* col, const double* mean, long long n,
+                    const double* bias, int n_sim, const double* size_factors,
+                    int sf_by_distance, int n_dist, const double* disp,
+                    int disp_per_pixel, int rep, unsigned long long seed,
+                    long long* counts_out, double* biased_mean_out,
+                    h3d_stream_t stream);
+
+/* perturb_cluster, hic3defdr/util/simulation.py:12-67, once the footprint of
+ * every cluster has been turned into (pixel key = row << 32 | col, factor)
+ * pairs: mean[pixel] *= factor for the pixels present in pixel_keys (sorted). */
+int h3d_perturb(const long long* pixel_keys, long long n_px, const long long* keys,
+                const double* factor, long long n, double* mean, h3d_stream_t stream);
+
+/* The iteration of kr_balance, hic3defdr/util/balancing.py:86-174, on a
+ * symmetric CSR matrix without empty rows (int32 indptr / indices, float64
+ * data, all on the device): returns the balancing vector x (device, n) with
+ * x_i x_j A_ij summing to 1 over every row, the residual after every outer
+ * iteration (host, at most res_cap values) and the number of SpMVs. */
+int h3d_kr_balance(const int* indptr, const int* indices, const double* data, int n,
+                   double tol, const double* x0, double delta, double ddelta,
+                   int max_iter, double* x_out, double* res_host, int res_cap,
+                   int* n_res_host, int* n_matvec_host, void* ws, size_t ws_bytes,
+                   h3d_stream_t stream);
+size_t h3d_kr_balance_ws_bytes(int n);
+
+/* filter_sparse_rows_count, hic3defdr/util/filtering.py:50-53: per bin of an
+ * upper-triangular CSR matrix (int64 indptr), the number of entries > 0 among
+ * its k nearest upstream (column i, rows i-k .. i-1) and downstream (row i,
+ * columns i+1 .. i+k) contacts. */
+int h3d_band_nnz(const long long* indptr, const int* indices, const double* data, int n,
+                 int k, int* upstream, int* downstream, h3d_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -319,9 +319,17 @@ def test_lpt_and_ranges():
     assert abs(loads[0] - loads[1]) <= 2
     keys, per = hd.distance_keys(201, 8)
     assert per == 26 and len(set(keys)) == 201 and keys.max() < 8 * per
-    for k in range(8):
-        d = hd.owned_distances(201, k, 8)
-        assert (d % 8 == k).all() and (keys[d] == k * per + np.arange(len(d))).all()
+    owned = [hd.owned_distances(201, k, 8) for k in range(8)]
+    assert sorted(np.concatenate(owned).tolist()) == list(range(201))
+    for k, d in enumerate(owned):
+        # one distance of every group of 8, dealt 0..7, 7..0, 0..7, ...
+        assert (d // 8 == np.arange(len(d))).all()
+        assert (np.where((d // 8) % 2 == 0, d % 8, 7 - d % 8) == k).all()
+        assert (keys[d] == k * per + np.arange(len(d))).all()
+    # the boustrophedon deal balances a cost that falls with the distance
+    cost = 1000.0 - 3.0 * np.arange(201)
+    loads = [cost[d].sum() for d in owned]
+    assert (max(loads) - min(loads)) / np.mean(loads) < 0.05
     keys, per = hd.distance_keys(7, 1)
     assert per == 7 and (keys == np.arange(7)).all()
 
