@@ -94,6 +94,10 @@ SIGNATURES = {
                                c_int, vp, vp, c_int, vp, vp, vp, c_sz, vp]),
     'h3d_kr_balance_ws_bytes': (c_sz, [c_int]),
     'h3d_band_nnz': (c_int, [vp, vp, vp, c_int, c_int, vp, vp, vp]),
+    'h3d_host_expand_by_distance': (c_int, [vp, c_int, c_int, vp, vp, vp, c_ll,
+                                            vp, c_int]),
+    'h3d_narrow_i64': (c_int, [vp, c_ll, vp, vp, vp]),
+    'h3d_host_widen_i32': (c_int, [vp, vp, c_ll, c_int]),
     'h3d_connected_components': (c_int, [vp, vp, c_ll, vp, vp, vp, c_sz, vp]),
     'h3d_connected_components_ws_bytes': (c_sz, [c_ll]),
 }

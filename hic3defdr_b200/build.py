@@ -69,7 +69,7 @@ def build(force=False, verbose=True):
     objs = [o for o, _ in results]
     rebuilt = any(r for _, r in results)
     if rebuilt or not os.path.exists(LIB):
-        cmd = [NVCC, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a',
+        cmd = [NVCC, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-Xcompiler', '-pthread',
                '-o', LIB] + objs
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:

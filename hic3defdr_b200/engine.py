@@ -144,7 +144,7 @@ def prepare_many(chrom_inputs, design, n_streams=None, sink=None, **kw):
         if sink is not None:
             with torch.cuda.stream(stream):
                 for k in PREPARE_OUTPUTS:
-                    sink(i, k, st[k])
+                    emit_output(sink, i, k, st)
 
     def advance():
         i, stream, gen, pending = active.pop(0)
@@ -410,8 +410,10 @@ def estimate_disp(states, design, dist_max, cond_names=None, estimator='qcml',
                                 auto_frac_factor, weighted_lowess, log)
         disp = ops.gather_table(dist_cat, table) if n_tot else torch.empty(
             (0, n_conds), dtype=torch.float64, device='cuda')
+    disp_table = ops.dev(table)
     for i, s in enumerate(states):
         s['disp'] = disp[offs[i]:offs[i + 1]]
+        s['disp_table'] = disp_table         # disp = disp_table[col - row]
     return disp_per_dist, fns, stats
 
 
@@ -443,8 +445,26 @@ def bh(states, use_loop_idx=False):
     return states
 
 
-PREPARE_OUTPUTS = ('row', 'col', 'raw', 'size_factors', 'scaled', 'disp_idx')
+PREPARE_OUTPUTS = ('row', 'col', 'disp_idx', 'raw', 'size_factors', 'scaled')
 LRT_OUTPUTS = ('pvalues', 'llr', 'mu_hat_null', 'mu_hat_alt')
+
+
+def emit_output(sink, i, name, st):
+    """Hands output ``name`` of chromosome state ``st`` to ``sink``.  A sink
+    that declares ``compact`` (staging.OutputDrain) receives the arrays that
+    are functions of the pixel distance as their per-distance tables and
+    ``raw`` through its narrowing entry; a plain callable gets every tensor."""
+    if sink is None:
+        return
+    if getattr(sink, 'compact', False):
+        if name == 'size_factors' and 'sf_table' in st:
+            return sink.table(i, name, st['sf_table'], int(st['row'].numel()))
+        if name == 'disp' and 'disp_table' in st:
+            return sink.table(i, name, st['disp_table'],
+                              int(st['disp_index'].numel()), mask='disp_idx')
+        if name == 'raw' and st['raw'].dtype == torch.int64:
+            return sink.narrow(i, name, st['raw'])
+    sink(i, name, st[name])
 
 
 def run_to_qvalues(chrom_inputs, design, dist_min=4, dist_max=200,
@@ -473,7 +493,7 @@ def run_to_qvalues(chrom_inputs, design, dist_min=4, dist_max=200,
             for i, (csr, b) in enumerate(chrom_inputs):
                 states.append(prepare_chrom_sharded(csr, b, design, **kw))
                 for k in PREPARE_OUTPUTS:
-                    emit(i, k, states[-1][k])
+                    emit_output(sink, i, k, states[-1])
         else:
             states = prepare_many(chrom_inputs, design, sink=sink, **kw)
     with stage('estimate_disp'):
@@ -482,7 +502,7 @@ def run_to_qvalues(chrom_inputs, design, dist_min=4, dist_max=200,
                                         auto_frac_factor=auto_frac_factor,
                                         weighted_lowess=weighted_lowess)
         for i, s in enumerate(states):
-            emit(i, 'disp', s['disp'])
+            emit_output(sink, i, 'disp', s)
     with stage('lrt'):
         failed = torch.zeros(1, dtype=torch.int32, device='cuda')
         for i, s in enumerate(states):

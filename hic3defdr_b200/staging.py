@@ -147,12 +147,30 @@ class InputPrefetcher(object):
         return len(self.host)
 
 
+_UNPACK_POOL = None
+
+
+def _unpack_pool():
+    global _UNPACK_POOL
+    if _UNPACK_POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _UNPACK_POOL = ThreadPoolExecutor(2)
+    return _UNPACK_POOL
+
+
 class OutputDrain(object):
     """``drain(i, name, tensor)``: device -> pinned host copy of a final
     output on a copy stream, ordered after the kernels that produced it.
-    ``wait()`` returns {(i, name): pinned tensor} once everything landed."""
+    ``wait()`` returns {(i, name): pinned tensor} once everything landed.
 
-    def __init__(self, pool=None, after=None):
+    ``compact`` (default): three arrays do not cross the link as they are
+    stored (csrc/hostpack.cu): ``size_factors`` and ``disp`` travel as their
+    per-distance tables and are rebuilt in the pinned output buffer by host
+    threads from ``row`` / ``col`` (/ ``disp_idx``), ``raw`` travels as int32
+    and is widened there.  Same arrays for the caller, 2.9 GB less on the wire
+    for the mouse genome; the rebuilding overlaps the dispersion estimate."""
+
+    def __init__(self, pool=None, after=None, compact=True, host_threads=None):
         """``after``: an ``InputPrefetcher`` whose uploads go first.  The two
         directions of the link share ~92 GB/s on this pool's hosts (55 GB/s
         each alone), and the uploads are on the critical path (the kernels wait
@@ -160,6 +178,7 @@ class OutputDrain(object):
         ~120 ms of dispersion estimation that follow; so the drain holds its
         copies back until every chromosome has been queued for upload and the
         last upload has finished."""
+        import os
         self.stream = torch.cuda.Stream()
         self.pool = pool if pool is not None else {}
         self.out = {}
@@ -167,42 +186,129 @@ class OutputDrain(object):
         self.nbytes = 0
         self.after = after
         self.held = []
+        self.compact = compact
+        self.jobs = []
+        self.host_threads = host_threads or max(
+            1, min(16, (os.cpu_count() or 1) // max(1, _world())))
 
+    # ---- entry points ---------------------------------------------------
     def __call__(self, i, name, tensor):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self._submit(lambda: self._copy(i, name, tensor, ev))
+
+    def table(self, i, name, table, n_rows, mask=None):
+        """the (n_rows, C) array ``table[col - row]`` of chromosome i (over the
+        pixels with ``mask`` set, the name of an output already handed in):
+        only the table crosses the link"""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self._submit(lambda: self._table(i, name, table, n_rows, mask, ev))
+
+    def narrow(self, i, name, tensor):
+        """an int64 array whose values fit 32 bits: copied as int32, widened
+        on the host (copied as it is if a value does not fit)"""
+        from hic3defdr_b200._native import lib, ptr
+        t32 = torch.empty(tensor.shape, dtype=torch.int32, device='cuda')
+        flag = torch.zeros(1, dtype=torch.int32, device='cuda')
+        lib().call('h3d_narrow_i64', ptr(tensor), tensor.numel(), ptr(t32),
+                   ptr(flag), torch.cuda.current_stream().cuda_stream)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self._submit(lambda: self._narrow(i, name, tensor, t32, flag, ev))
+
+    def _submit(self, fn):
         if self.after is not None:
-            ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream())
-            self.held.append((i, name, tensor, ev))
+            self.held.append(fn)
             if self.after.n_issued < len(self.after.host):
                 return
             self.stream.wait_event(self.after.uploaded)
             held, self.held, self.after = self.held, [], None
-            for j, nm, t, e in held:
-                self._copy(j, nm, t, e)
+            for f in held:
+                f()
             return
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream())
-        self._copy(i, name, tensor, ev)
+        fn()
 
-    def _copy(self, i, name, tensor, ev):
-        key = (i, name)
+    # ---- copies ---------------------------------------------------------
+    def _host(self, key, shape, dtype):
         host = self.pool.get(key)
-        if host is None or host.shape != tensor.shape or \
-                host.dtype != tensor.dtype:
-            host = torch.empty(tensor.shape, dtype=tensor.dtype).pin_memory()
+        if host is None or tuple(host.shape) != tuple(shape) or \
+                host.dtype != dtype:
+            host = torch.empty(tuple(shape), dtype=dtype).pin_memory()
             self.pool[key] = host
+        return host
+
+    def _copy(self, i, name, tensor, ev, publish=True):
+        key = (i, name)
+        host = self._host(key, tensor.shape, tensor.dtype)
         self.stream.wait_event(ev)
         with torch.cuda.stream(self.stream):
             host.copy_(tensor, non_blocking=True)
         self.keep.append(tensor)
-        self.out[key] = host
+        if publish:
+            self.out[key] = host
         self.nbytes += tensor.numel() * tensor.element_size()
+        return host
+
+    def _landed(self):
+        ev = torch.cuda.Event()
+        ev.record(self.stream)
+        return ev
+
+    def _table(self, i, name, table, n_rows, mask, ev):
+        from hic3defdr_b200._native import lib, ptr
+        th = self._copy(i, name + '__table', table, ev, publish=False)
+        out = self._host((i, name), (n_rows, table.shape[1]), torch.float64)
+        self.out[(i, name)] = out
+        row, col = self.out[(i, 'row')], self.out[(i, 'col')]
+        m = self.out[(i, mask)] if mask else None
+        landed = self._landed()          # row, col, mask and the table are in
+        n_threads = self.host_threads
+
+        def job():
+            landed.synchronize()
+            lib().call('h3d_host_expand_by_distance', ptr(th), th.shape[0],
+                       th.shape[1], ptr(row), ptr(col), ptr(m), row.numel(),
+                       ptr(out), n_threads)
+        self.jobs.append(_unpack_pool().submit(job))
+
+    def _narrow(self, i, name, tensor, t32, flag, ev):
+        from hic3defdr_b200._native import lib, ptr
+        h32 = self._copy(i, name + '__i32', t32, ev, publish=False)
+        hflag = self._copy(i, name + '__overflow', flag, ev, publish=False)
+        out = self._host((i, name), tensor.shape, torch.int64)
+        self.out[(i, name)] = out
+        landed = self._landed()
+        n_threads = self.host_threads
+
+        def job():
+            landed.synchronize()
+            if int(hflag[0]):
+                return (i, name, tensor)         # redo as a plain copy
+            lib().call('h3d_host_widen_i32', ptr(h32), ptr(out), h32.numel(),
+                       n_threads)
+        self.keep.append(tensor)
+        self.jobs.append(_unpack_pool().submit(job))
 
     def wait(self):
         if self.held:                  # uploads never completed the hand-over
             held, self.held, self.after = self.held, [], None
-            for j, nm, t, e in held:
-                self._copy(j, nm, t, e)
+            for f in held:
+                f()
         self.stream.synchronize()
+        redo = [r for r in (j.result() for j in self.jobs) if r is not None]
+        self.jobs = []
+        for i, name, tensor in redo:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            self._copy(i, name, tensor, ev)
+        if redo:
+            self.stream.synchronize()
         self.keep = []
         return self.out
+
+
+def _world():
+    import torch.distributed as td
+    return td.get_world_size() if td.is_available() and td.is_initialized() \
+        else 1

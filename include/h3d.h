@@ -455,6 +455,24 @@ size_t h3d_kr_balance_ws_bytes(int n);
 int h3d_band_nnz(const long long* indptr, const int* indices, const double* data, int n,
                  int k, int* upstream, int* downstream, h3d_stream_t stream);
 
+/* ---- compact transfer of redundant outputs ------------------------------- */
+
+/* size_factors (N, R) and disp (N_d, C) are functions of the pixel distance
+ * (hic3defdr/util/scaling.py:92-104, analysis/analysis.py:218): the end-to-end
+ * path copies the per-distance table to the host and rebuilds the array there.
+ * HOST pointers: out[k, :] = table[col[i] - row[i], :] over the pixels with
+ * mask[i] != 0 (all pixels when mask is NULL), with n_threads host threads. */
+int h3d_host_expand_by_distance(const double* table, int n_rows, int n_cols,
+                                const int* row, const int* col,
+                                const unsigned char* mask, long long n,
+                                double* out, int n_threads);
+/* raw (N, R) is int64 in the reference's files (analysis/analysis.py:92-96)
+ * but holds counts: narrowed on the device (overflow: device int, set when a
+ * value does not fit 32 bits), widened again into the host buffer. */
+int h3d_narrow_i64(const long long* in, long long n, int* out, int* overflow,
+                   h3d_stream_t stream);
+int h3d_host_widen_i32(const int* in, long long* out, long long n, int n_threads);
+
 #ifdef __cplusplus
 }
 #endif

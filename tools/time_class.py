@@ -2,7 +2,11 @@
 per step: SURVEY.md section 8(d) "end-to-end" clock for BASELINE configs[0]
 (chr18 + chr19, mouse-sized, 10 kb, 2-vs-2).
 
-    python tools/time_class.py [workdir] [--chroms chr18,chr19]
+    python tools/time_class.py [workdir] [--chroms=chr18,chr19 | --chroms=all]
+
+``--chroms=all``: BASELINE configs[1], the whole mouse genome (20 chromosomes,
+48.4 M union pixels, ~2.3 GB of .npz in, ~8.2 GB of .npy out): only the
+one-call ``run_to_qvalues`` is timed (twice: cold, then with a warm page cache).
 """
 import json
 import os
@@ -21,16 +25,19 @@ def main():
     args = [a for a in sys.argv[1:] if not a.startswith('--')]
     root = args[0] if args else tempfile.mkdtemp(prefix='h3d_class_')
     chroms = ['chr18', 'chr19']
+    genome = False
     for a in sys.argv[1:]:
         if a.startswith('--chroms'):
             chroms = a.split('=', 1)[1].split(',')
+            if chroms == ['all']:
+                chroms, genome = list(MM10_10KB), True
     t0 = time.perf_counter()
     kw = write_dataset(os.path.join(root, 'in'),
                        {c: MM10_10KB[c] for c in chroms}, n_reps=4,
                        dist_max=200, config=1)
     t_gen = time.perf_counter() - t0
     out = {}
-    for trial in range(2):           # second pass: page cache and CUDA context warm
+    for trial in range(0 if genome else 2):   # second pass: page cache and CUDA context warm
         outdir = os.path.join(root, 'out%d' % trial)
         h = HiC3DeFDR(outdir=outdir, dist_thresh_max=200, **kw)
         times = {}
@@ -50,14 +57,25 @@ def main():
                                       output_bytes=nbytes,
                                       pixels_per_s=round(n_px / times['total']))
     # the whole pipeline in one call: writers of a step overlap the next step
-    outdir = os.path.join(root, 'out_all')
-    h = HiC3DeFDR(outdir=outdir, dist_thresh_max=200, **kw)
-    t = time.perf_counter()
-    h.run_to_qvalues()
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t
-    out['run_to_qvalues'] = dict(total=round(dt, 3),
-                                 pixels_per_s=round(n_px / dt))
+    import shutil
+    for trial in range(2):
+        outdir = os.path.join(root, 'out_all')
+        shutil.rmtree(outdir, ignore_errors=True)
+        h = HiC3DeFDR(outdir=outdir, dist_thresh_max=200, **kw)
+        t = time.perf_counter()
+        h.run_to_qvalues()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t
+        n_px = sum(len(h.load_data('row', c)) for c in chroms)
+        nbytes = sum(os.path.getsize(os.path.join(outdir, f))
+                     for f in os.listdir(outdir))
+        in_bytes = sum(os.path.getsize(p.replace('<chrom>', c))
+                       for p in kw['raw_npz_patterns'] + kw['bias_patterns']
+                       for c in chroms)
+        out['run_to_qvalues_%d' % trial] = dict(
+            total=round(dt, 3), union_pixels=n_px, input_bytes=in_bytes,
+            output_bytes=nbytes, pixels_per_s=round(n_px / dt))
+        del h
     out['generate_inputs_s'] = round(t_gen, 1)
     print(json.dumps(out))
 
