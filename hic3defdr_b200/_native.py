@@ -70,6 +70,9 @@ SIGNATURES = {
     'h3d_lowess': (c_int, [vp, vp, c_int, c_dbl, c_int, c_dbl, vp, vp, c_sz,
                            vp]),
     'h3d_lowess_ws_bytes': (c_sz, [c_int]),
+    'h3d_lowess_batch': (c_int, [vp, vp, vp, vp, vp, c_int, vp, c_int, vp, vp,
+                                 c_sz, vp]),
+    'h3d_lowess_batch_ws_bytes': (c_sz, [c_int, c_int]),
     'h3d_gather_table': (c_int, [vp, c_ll, vp, c_int, c_int, vp, vp]),
     'h3d_fit_mu_hat': (c_int, [vp, vp, vp, c_ll, c_ll, c_ll, c_int, vp, vp,
                                vp]),

@@ -290,57 +290,66 @@ equalize_kernel(const double* __restrict__ x, const double* __restrict__ f, long
     }
 }
 
-// Order-independent sums.  Every per-pixel term is converted to a 128-bit
-// fixed-point number (64 integer bits, 64 fractional bits; the conversion is a
-// pure function of the value) and the terms are added as integers, which is
-// associative and commutative: the sum of a bin does not depend on how its
-// pixels are ordered, chunked, or spread over thread blocks -- and therefore not
-// on how many GPUs pooled them.  Non-finite terms (and
-// anything beyond +-2^62) are counted in ``bad`` instead.
+// Order-independent sums.  Every per-pixel term v is split, exactly, into a
+// multiple of 2^-10 and a multiple of 2^-58 below it (two additions of a
+// "magic" constant put the integer into the low mantissa bits: no conversion
+// instruction), and the two integers are added in 64-bit integer arithmetic,
+// which is associative and commutative: the sum of a bin does not depend on how
+// its pixels are ordered, chunked, or spread over thread blocks -- and
+// therefore not on how many GPUs pooled them.  What is
+// dropped of a term is below 2^-59 (4e-18) whatever its size.  Terms that are
+// not finite or reach 2^40 are counted in ``bad`` instead.
 struct Fix128 {
-    unsigned long long lo;   // fractional part, units of 2^-64
-    long long hi;            // integer part (floor)
+    unsigned long long lo;   // units of 2^-58, kept in [0, 2^48) between blocks
+    long long hi;            // units of 2^-10
     long long bad;           // number of non-representable terms
     long long cnt;           // number of terms (used by the MME mean)
 };
 
 // per-thread accumulator (registers): count-free, 32-bit flag
-struct FixAcc { unsigned long long lo; long long hi; int bad; };
+struct FixAcc { long long lo, hi; int bad; };
 
 __device__ __forceinline__ void fix_add(FixAcc& a, double v) {
-    if (!(fabs(v) < 4.611686018427387904e18)) { a.bad += 1; return; }
-    const double fl = floor(v);
-    const unsigned long long l = __double2ull_rz((v - fl) * 18446744073709551616.0);
-    a.lo += l;
-    a.hi += __double2ll_rz(fl) + (long long)(a.lo < l);
+    constexpr double kM1 = 6597069766656.0;          // 1.5 * 2^42: ulp 2^-10
+    constexpr double kM2 = 0.0234375;                // 1.5 * 2^-6:  ulp 2^-58
+    if (!(fabs(v) < 1099511627776.0)) { a.bad += 1; return; }       // 2^40
+    const double t1 = v + kM1;                       // rounds v to a multiple of 2^-10
+    const double e = v - (t1 - kM1);                 // exact, |e| <= 2^-11
+    const double t2 = e + kM2;                       // rounds e to a multiple of 2^-58
+    a.hi += __double_as_longlong(t1) - __double_as_longlong(kM1);
+    a.lo += __double_as_longlong(t2) - __double_as_longlong(kM2);
 }
 
 __host__ __device__ __forceinline__ double fix_value(const Fix128& a) {
-    return (double)a.hi + (double)a.lo * 5.421010862427522170e-20;     // 2^-64
+    return (double)a.hi * 9.765625e-4 + (double)a.lo * 3.469446951953614189e-18;   // 2^-10, 2^-58
 }
 
 // block-wide sum of the threads' accumulators (and of a per-thread term
-// count); the result is valid in thread 0
+// count), normalised (lo in [0, 2^48)); the result is valid in thread 0
 __device__ __forceinline__ Fix128 block_sum_fix(FixAcc v, int cnt, Fix128* sh) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long lo = __shfl_down_sync(0xffffffffu, v.lo, o);
-        const long long hi = __shfl_down_sync(0xffffffffu, v.hi, o);
+        v.lo += __shfl_down_sync(0xffffffffu, v.lo, o);
+        v.hi += __shfl_down_sync(0xffffffffu, v.hi, o);
         v.bad += __shfl_down_sync(0xffffffffu, v.bad, o);
         cnt += __shfl_down_sync(0xffffffffu, cnt, o);
-        v.lo += lo;
-        v.hi += hi + (long long)(v.lo < lo);
     }
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = Fix128{v.lo, v.hi, (long long)v.bad, (long long)cnt};
+    if ((threadIdx.x & 31) == 0)
+        sh[threadIdx.x >> 5] = Fix128{(unsigned long long)v.lo, v.hi, (long long)v.bad, (long long)cnt};
     __syncthreads();
     Fix128 t = {0ull, 0ll, 0ll, 0ll};
-    if (threadIdx.x == 0)
+    if (threadIdx.x == 0) {
+        long long lo = 0;
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
-            t.lo += sh[w].lo;
-            t.hi += sh[w].hi + (long long)(t.lo < sh[w].lo);
+            lo += (long long)sh[w].lo;
+            t.hi += sh[w].hi;
             t.bad += sh[w].bad;
             t.cnt += sh[w].cnt;
         }
+        const long long carry = lo >> 48;            // floor: 2^48 units of 2^-58 = one of 2^-10
+        t.hi += carry;
+        t.lo = (unsigned long long)(lo - (carry << 48));
+    }
     return t;
 }
 
@@ -362,15 +371,12 @@ __device__ __forceinline__ Fix128 block_sum_fix(FixAcc v, int cnt, Fix128* sh) {
 #endif
 
 // adds a block's total to the (segment, condition) accumulator; integer
-// atomics commute, so the result is exact whatever the arrival order
+// atomics commute, so the result is exact whatever the arrival order (every
+// block contributes lo < 2^48: no overflow below 2^15 chunks = 32 M pixels of
+// one bin, and hi has 2^53 units of headroom)
 __device__ __forceinline__ void fix_atomic_add(Fix128* dst, const Fix128& t) {
-    if (t.lo) {
-        const unsigned long long old = atomicAdd(&dst->lo, t.lo);
-        const long long carry = (long long)(old + t.lo < old);
-        if (t.hi + carry) atomicAdd((unsigned long long*)&dst->hi, (unsigned long long)(t.hi + carry));
-    } else if (t.hi) {
-        atomicAdd((unsigned long long*)&dst->hi, (unsigned long long)t.hi);
-    }
+    if (t.lo) atomicAdd(&dst->lo, t.lo);
+    if (t.hi) atomicAdd((unsigned long long*)&dst->hi, (unsigned long long)t.hi);
     if (t.bad) atomicAdd((unsigned long long*)&dst->bad, (unsigned long long)t.bad);
     if (t.cnt) atomicAdd((unsigned long long*)&dst->cnt, (unsigned long long)t.cnt);
 }
@@ -394,7 +400,7 @@ nll_kernel(const double* __restrict__ pseudo, long long ld, const int* __restric
     const long long lo = chunk_lo[blockIdx.x];
     const long long hi = chunk_hi[blockIdx.x];
     const double* __restrict__ base = pseudo + (long long)cr.pseudo_row[c] * ld;
-    FixAcc a = {0ull, 0ll, 0};
+    FixAcc a = {0ll, 0ll, 0};
     if (r >= 10.0) {
         for (long long i = lo + threadIdx.x; i < hi; i += 256) {
             double z = 0.0, t = 0.0;
@@ -443,7 +449,7 @@ mme_kernel(const double* __restrict__ x, const double* __restrict__ f, long long
     const long long lo = chunk_lo[blockIdx.x];
     const long long hi = chunk_hi[blockIdx.x];
     const int nr = cr.n_in[c];
-    FixAcc a = {0ull, 0ll, 0};
+    FixAcc a = {0ll, 0ll, 0};
     int n_est = 0;
     for (long long i = lo + threadIdx.x; i < hi; i += 256) {
         double v[MAXRC];

@@ -33,10 +33,29 @@ __device__ __forceinline__ double warp_sum_all(double v) {
     return v;
 }
 
+// one smoothing problem of a batch: its slice [off, off + n) of the packed
+// arrays (x, y in; y_fit out; scratch of the same layout)
+struct LowessJob { int off, n, k_nn, n_pass; double delta; };
+
 __global__ void __launch_bounds__(kLwThreads)
-lowess_kernel(const double* __restrict__ x, const double* __restrict__ y, int n, int k_nn, int n_pass,
-              double delta, double* __restrict__ y_fit, double* __restrict__ resid_w,
-              double* __restrict__ resid, double* __restrict__ fitv, LowessPlan plan) {
+lowess_kernel(const double* __restrict__ x_all, const double* __restrict__ y_all,
+              const LowessJob* __restrict__ jobs, double* __restrict__ y_fit_all,
+              double* __restrict__ resid_w_all, double* __restrict__ resid_all,
+              double* __restrict__ fitv_all, LowessPlan plan_all) {
+    const LowessJob job = jobs[blockIdx.x];
+    const int n = job.n, k_nn = job.k_nn, n_pass = job.n_pass;
+    const double delta = job.delta;
+    const double* __restrict__ x = x_all + job.off;
+    const double* __restrict__ y = y_all + job.off;
+    double* __restrict__ y_fit = y_fit_all + job.off;
+    double* __restrict__ resid_w = resid_w_all + job.off;
+    double* __restrict__ resid = resid_all + job.off;
+    double* __restrict__ fitv = fitv_all + job.off;
+    LowessPlan plan;
+    plan.anchor = plan_all.anchor + 3 * job.off;
+    plan.a0 = plan_all.a0 + job.off;
+    plan.a1 = plan_all.a1 + job.off;
+    plan.al = plan_all.al + job.off;
     __shared__ int s_n_anchor;
     __shared__ double s_med[2];
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
@@ -155,30 +174,73 @@ lowess_kernel(const double* __restrict__ x, const double* __restrict__ y, int n,
 
 using namespace h3d;
 
-extern "C" size_t h3d_lowess_ws_bytes(int n) { return 4 * ws_pad((size_t)n * 8) + ws_pad((size_t)n * 12) + 2 * ws_pad((size_t)n * 4); }
+extern "C" size_t h3d_lowess_ws_bytes(int n) { return 4 * ws_pad((size_t)n * 8) + ws_pad((size_t)n * 12) + 2 * ws_pad((size_t)n * 4) + 256; }
+
+static int lowess_launch(const double* x, const double* y, int n_total, const LowessJob* jobs_dev,
+                         int n_jobs, double* y_fit, void* ws, size_t ws_bytes, cudaStream_t st) {
+    Workspace w(ws, ws_bytes);
+    double* resid_w = w.take<double>(n_total);
+    double* resid = w.take<double>(n_total);
+    double* fitv = w.take<double>(n_total);
+    LowessPlan plan;
+    plan.al = w.take<double>(n_total);
+    plan.anchor = w.take<int>((size_t)3 * n_total);
+    plan.a0 = w.take<int>(n_total);
+    plan.a1 = w.take<int>(n_total);
+    if (!resid_w || !resid || !fitv || !plan.al || !plan.anchor || !plan.a0 || !plan.a1) {
+        set_error("lowess workspace too small");
+        return H3D_ERR_WORKSPACE;
+    }
+    lowess_kernel<<<n_jobs, kLwThreads, 0, st>>>(x, y, jobs_dev, y_fit, resid_w, resid, fitv, plan);
+    H3D_LAUNCHED("lowess_kernel");
+    return H3D_OK;
+}
+
+static int lowess_k(double frac, int n) {
+    int k = (int)(frac * (double)n + 1e-10);
+    if (k < 2) k = 2;
+    if (k > n) k = n;
+    return k;
+}
 
 extern "C" int h3d_lowess(const double* x, const double* y, int n, double frac, int it, double delta,
                           double* y_fit, void* ws, size_t ws_bytes, h3d_stream_t stream) {
     H3D_REQUIRE(n >= 2, "lowess needs at least two points");
     H3D_REQUIRE(it >= 0, "negative number of robustifying iterations");
-    Workspace w(ws, ws_bytes);
-    double* resid_w = w.take<double>(n);
-    double* resid = w.take<double>(n);
-    double* fitv = w.take<double>(n);
-    LowessPlan plan;
-    plan.al = w.take<double>(n);
-    plan.anchor = w.take<int>((size_t)3 * n);
-    plan.a0 = w.take<int>(n);
-    plan.a1 = w.take<int>(n);
-    if (!resid_w || !resid || !fitv || !plan.al || !plan.anchor || !plan.a0 || !plan.a1) {
-        set_error("lowess workspace too small");
-        return H3D_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    // the job descriptor lives at the end of the workspace
+    H3D_REQUIRE(ws_bytes >= h3d_lowess_ws_bytes(n), "lowess workspace too small");
+    LowessJob job = {0, n, lowess_k(frac, n), it + 1, delta};
+    LowessJob* job_dev = (LowessJob*)((char*)ws + h3d_lowess_ws_bytes(n) - 256);
+    H3D_CHECK(cudaMemcpyAsync(job_dev, &job, sizeof(job), cudaMemcpyHostToDevice, st));
+    H3D_CHECK(cudaStreamSynchronize(st));      // the descriptor is on the stack
+    return lowess_launch(x, y, n, job_dev, 1, y_fit, ws, ws_bytes - 256, st);
+}
+
+// n_jobs independent smoothing problems in one launch (one thread block each):
+// problem j is the slice [off[j], off[j] + n[j]) of the packed x / y / y_fit.
+// off_host, n_host, frac_host, delta_host: HOST arrays.
+extern "C" size_t h3d_lowess_batch_ws_bytes(int n_total, int n_jobs) {
+    return h3d_lowess_ws_bytes(n_total) + ws_pad((size_t)n_jobs * sizeof(LowessJob));
+}
+
+extern "C" int h3d_lowess_batch(const double* x, const double* y, const int* off_host,
+                                const int* n_host, const double* frac_host, int it,
+                                const double* delta_host, int n_jobs, double* y_fit, void* ws,
+                                size_t ws_bytes, h3d_stream_t stream) {
+    H3D_REQUIRE(n_jobs >= 1 && n_jobs <= 64 && it >= 0, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    LowessJob jobs[64];
+    int n_total = 0;
+    for (int j = 0; j < n_jobs; ++j) {
+        H3D_REQUIRE(n_host[j] >= 2, "lowess needs at least two points");
+        jobs[j] = {off_host[j], n_host[j], lowess_k(frac_host[j], n_host[j]), it + 1, delta_host[j]};
+        if (off_host[j] + n_host[j] > n_total) n_total = off_host[j] + n_host[j];
     }
-    int k = (int)(frac * (double)n + 1e-10);
-    if (k < 2) k = 2;
-    if (k > n) k = n;
-    lowess_kernel<<<1, kLwThreads, 0, (cudaStream_t)stream>>>(x, y, n, k, it + 1, delta, y_fit, resid_w,
-                                                             resid, fitv, plan);
-    H3D_LAUNCHED("lowess_kernel");
-    return H3D_OK;
+    H3D_REQUIRE(ws_bytes >= h3d_lowess_batch_ws_bytes(n_total, n_jobs), "lowess workspace too small");
+    const size_t main_bytes = h3d_lowess_ws_bytes(n_total) - 256;
+    LowessJob* jobs_dev = (LowessJob*)((char*)ws + main_bytes);
+    H3D_CHECK(cudaMemcpyAsync(jobs_dev, jobs, (size_t)n_jobs * sizeof(LowessJob), cudaMemcpyHostToDevice, st));
+    H3D_CHECK(cudaStreamSynchronize(st));      // the descriptors are on the stack
+    return lowess_launch(x, y, n_total, jobs_dev, n_jobs, y_fit, ws, main_bytes, st);
 }

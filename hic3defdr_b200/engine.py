@@ -18,7 +18,7 @@ import torch
 from hic3defdr_b200 import dist as hdist
 from hic3defdr_b200 import ops
 from hic3defdr_b200.trace import stage
-from hic3defdr_b200.trend import lowess_fit, weighted_lowess_fit
+from hic3defdr_b200.trend import fit_many
 
 
 def prepare_chrom_steps(csr, bias_raw, design, dist_min=4, dist_max=200,
@@ -291,21 +291,18 @@ def pool_to_owners(states, dist_max, n_reps):
     return x, f, dist_cat, runs, offs, per
 
 
-_TREND_STREAMS = {}
-_TREND_POOL = None
-
-
 def fit_trends(disp_per_dist, dist_max, cond_names, frac=None,
                auto_frac_factor=15., weighted_lowess=True, log=None):
     """analysis/analysis.py:208-218: one trend per condition; returns
-    (list of callables, (dist_max + 1, C) table of their values)."""
-    lowess_fn = weighted_lowess_fit if weighted_lowess else lowess_fit
+    (list of callables, (dist_max + 1, C) table of their values).  The
+    smoothing of all conditions is one kernel launch (trend.fit_many)."""
     n_conds = disp_per_dist.shape[1]
     table = np.full((dist_max + 1, n_conds), np.nan)
-    device = torch.cuda.current_device()
-
-    def fit_one(c):
-        torch.cuda.set_device(device)        # the current device is per thread
+    specs = []
+    for c in range(n_conds):
+        if log:
+            log('  estimating dispersion for condition %s' % cond_names[c])
+            log('  fitting distance vs dispersion relationship')
         idx = np.isfinite(disp_per_dist[:, c])
         xs = np.arange(dist_max + 1)[idx]
         ys = disp_per_dist[:, c][idx]
@@ -314,32 +311,11 @@ def fit_trends(disp_per_dist, dist_max, cond_names, frac=None,
             kwargs['frac'] = frac
         if weighted_lowess:
             kwargs['auto_frac_factor'] = auto_frac_factor
-        # own stream: the (latency-bound) smoothing kernels of the conditions
-        # overlap instead of queueing behind each other
-        key = (device, c)
-        if key not in _TREND_STREAMS:       # persistent: their allocator pools stay warm
-            _TREND_STREAMS[key] = torch.cuda.Stream()
-        with torch.cuda.stream(_TREND_STREAMS[key]):
-            fn = lowess_fn(xs, ys, **kwargs)
-        return fn, fn(np.arange(dist_max + 1))
-
-    if log:
-        for c in range(n_conds):
-            log('  estimating dispersion for condition %s' % cond_names[c])
-            log('  fitting distance vs dispersion relationship')
-    torch.cuda.current_stream().synchronize()
-    if n_conds > 1:
-        global _TREND_POOL
-        if _TREND_POOL is None or _TREND_POOL._max_workers < n_conds:
-            import concurrent.futures       # persistent: thread start-up is
-            _TREND_POOL = concurrent.futures.ThreadPoolExecutor(n_conds)  # ~0.2 ms each
-        results = list(_TREND_POOL.map(fit_one, range(n_conds)))
-    else:
-        results = [fit_one(0)]
-    fns = []
-    for c, (fn, col) in enumerate(results):
-        table[:, c] = col
-        fns.append(fn)
+        specs.append((xs, ys, kwargs))
+    fns = fit_many(specs, weighted=weighted_lowess)
+    grid = np.arange(dist_max + 1)
+    for c, fn in enumerate(fns):
+        table[:, c] = fn(grid)
     return fns, table
 
 

@@ -97,47 +97,63 @@ def point_multiplicities(y_sorted, w=20, power=0.25):
     return np.floor(scaled).astype(int), max_w, np.nanmean(weight)
 
 
-def _device_lowess(x, y, frac, delta_frac, it=3):
-    """sorted-x lowess on the GPU; returns (x_sorted, y_fit)."""
-    import torch
-    from hic3defdr_b200._native import lib, ptr
+def _sorted_finite(x, y):
     ok = np.isfinite(x) & np.isfinite(y)
     x, y = x[ok], y[ok]
     order = np.argsort(x, kind='stable')
-    x, y = np.ascontiguousarray(x[order]), np.ascontiguousarray(y[order])
-    n = len(x)
-    delta = (np.nanmax(x) - np.nanmin(x)) * delta_frac
-    xd = torch.from_numpy(x).cuda()
-    yd = torch.from_numpy(y).cuda()
-    out = torch.empty(n, dtype=torch.float64, device='cuda')
-    wsb = lib().query('h3d_lowess_ws_bytes', n)
-    ws = torch.empty(wsb, dtype=torch.uint8, device='cuda')
-    lib().call('h3d_lowess', ptr(xd), ptr(yd), n, float(frac), int(it),
-               float(delta), ptr(out), ptr(ws), wsb,
-               torch.cuda.current_stream().cuda_stream)
+    return np.ascontiguousarray(x[order]), np.ascontiguousarray(y[order])
+
+
+def _device_lowess_batch(jobs, it=3):
+    """jobs: list of (x, y, frac, delta_frac); all smoothed in ONE kernel launch
+    (one thread block per job; one upload, one read-back).  Returns a list of
+    (x_sorted, y_fit)."""
+    import torch
+    from hic3defdr_b200._native import lib, ptr
     from hic3defdr_b200.ops import to_host
-    return x, to_host(out)
+    xs, ys, offs, ns, fracs, deltas = [], [], [], [], [], []
+    total = 0
+    for x, y, frac, delta_frac in jobs:
+        x, y = _sorted_finite(np.asarray(x, float), np.asarray(y, float))
+        xs.append(x)
+        ys.append(y)
+        offs.append(total)
+        ns.append(len(x))
+        fracs.append(float(frac))
+        deltas.append((np.nanmax(x) - np.nanmin(x)) * delta_frac)
+        total += (len(x) + 31) // 32 * 32
+    packed = np.zeros((2, total))
+    for x, y, o in zip(xs, ys, offs):
+        packed[0, o:o + len(x)] = x
+        packed[1, o:o + len(x)] = y
+    dev = torch.from_numpy(packed).cuda()
+    out = torch.empty(total, dtype=torch.float64, device='cuda')
+    wsb = lib().query('h3d_lowess_batch_ws_bytes', total, len(jobs))
+    ws = torch.empty(wsb, dtype=torch.uint8, device='cuda')
+    i32 = lambda v: np.ascontiguousarray(v, dtype=np.int32)
+    f64 = lambda v: np.ascontiguousarray(v, dtype=np.float64)
+    o_h, n_h, f_h, d_h = i32(offs), i32(ns), f64(fracs), f64(deltas)
+    lib().call('h3d_lowess_batch', ptr(dev[0]), ptr(dev[1]), ptr(o_h),
+               ptr(n_h), ptr(f_h), int(it), ptr(d_h), len(jobs), ptr(out),
+               ptr(ws), wsb, torch.cuda.current_stream().cuda_stream)
+    fit = to_host(out) if total * 8 <= 65536 else out.cpu().numpy()
+    return [(x, fit[o:o + len(x)].copy()) for x, o in zip(xs, offs)]
 
 
-def lowess_fit(x, y, logx=False, logy=False, left_boundary=None,
-               right_boundary=None, frac=0.3, delta=0.01):
-    """hic3defdr/util/lowess.py:10-92."""
+def _device_lowess(x, y, frac, delta_frac, it=3):
+    """sorted-x lowess on the GPU; returns (x_sorted, y_fit)."""
+    return _device_lowess_batch([(x, y, frac, delta_frac)], it=it)[0]
+
+
+def _plain_job(x, y, logx, logy, frac, delta):
     x = np.asarray(x, dtype=float)
     y = np.asarray(y, dtype=float)
-    fx = np.log(x) if logx else x
-    fy = np.log(y) if logy else y
-    sx, sy = _device_lowess(fx, fy, frac, delta)
-    _, ui = np.unique(sx, return_index=True)
-    return DispersionTrend(x, y, 0, sx[ui], sy[ui], frac, left_boundary,
-                           right_boundary, weighted=False, logx=logx,
-                           logy=logy)
+    job = (np.log(x) if logx else x, np.log(y) if logy else y, frac, delta)
+    return job, dict(x=x, y=y, inc=0, frac=frac, weighted=False)
 
 
-def weighted_lowess_fit(x, y, logx=False, logy=False, left_boundary=None,
-                        right_boundary=None, frac=None, auto_frac_factor=15.,
-                        delta=0.01, w=20, power=1. / 4,
-                        interpolate_before_increase=True):
-    """hic3defdr/util/lowess.py:95-244."""
+def _weighted_job(x, y, logx, logy, frac, auto_frac_factor, delta, w, power,
+                  interpolate_before_increase, messages):
     x = np.asarray(x, dtype=float)
     y = np.asarray(y, dtype=float)
     order = np.argsort(x)
@@ -149,11 +165,64 @@ def weighted_lowess_fit(x, y, logx=False, logy=False, left_boundary=None,
     ey = np.repeat(y[inc:], mult[inc:])
     if frac is None:
         frac = max(min(auto_frac_factor / (max_w * mean_w), 2. / 3), 0.05)
-        print('  using auto-determined lowess fraction of %.3f' % frac,
-              file=sys.stderr)
-    fx = np.log(ex) if logx else ex
-    fy = np.log(ey) if logy else ey
-    sx, sy = _device_lowess(fx, fy, frac, delta)
+        messages.append('  using auto-determined lowess fraction of %.3f'
+                        % frac)
+    job = (np.log(ex) if logx else ex, np.log(ey) if logy else ey, frac, delta)
+    return job, dict(x=x, y=y, inc=inc, frac=frac, weighted=True)
+
+
+def _finish(info, sx, sy, left_boundary, right_boundary, logx, logy):
     _, ui = np.unique(sx, return_index=True)
-    return DispersionTrend(x, y, inc, sx[ui], sy[ui], frac, left_boundary,
-                           right_boundary, weighted=True, logx=logx, logy=logy)
+    return DispersionTrend(info['x'], info['y'], info['inc'], sx[ui], sy[ui],
+                           info['frac'], left_boundary, right_boundary,
+                           weighted=info['weighted'], logx=logx, logy=logy)
+
+
+def fit_many(specs, weighted=True):
+    """One trend per (x, y, kwargs) in ``specs`` -- the kwargs of
+    ``weighted_lowess_fit`` / ``lowess_fit`` -- with every smoothing in the
+    same kernel launch.  Returns the list of callables."""
+    jobs, infos, msgs = [], [], []
+    for x, y, kw in specs:
+        kw = dict(kw)
+        logx, logy = kw.pop('logx', False), kw.pop('logy', False)
+        lb, rb = kw.pop('left_boundary', None), kw.pop('right_boundary', None)
+        if weighted:
+            job, info = _weighted_job(
+                x, y, logx, logy, kw.get('frac'),
+                kw.get('auto_frac_factor', 15.), kw.get('delta', 0.01),
+                kw.get('w', 20), kw.get('power', 1. / 4),
+                kw.get('interpolate_before_increase', True), msgs)
+        else:
+            job, info = _plain_job(x, y, logx, logy, kw.get('frac', 0.3),
+                                   kw.get('delta', 0.01))
+        info.update(lb=lb, rb=rb, logx=logx, logy=logy)
+        jobs.append(job)
+        infos.append(info)
+    for m in msgs:
+        print(m, file=sys.stderr)
+    fits = _device_lowess_batch(jobs)
+    return [_finish(i, sx, sy, i['lb'], i['rb'], i['logx'], i['logy'])
+            for i, (sx, sy) in zip(infos, fits)]
+
+
+def lowess_fit(x, y, logx=False, logy=False, left_boundary=None,
+               right_boundary=None, frac=0.3, delta=0.01):
+    """hic3defdr/util/lowess.py:10-92."""
+    return fit_many([(x, y, dict(logx=logx, logy=logy,
+                                 left_boundary=left_boundary,
+                                 right_boundary=right_boundary, frac=frac,
+                                 delta=delta))], weighted=False)[0]
+
+
+def weighted_lowess_fit(x, y, logx=False, logy=False, left_boundary=None,
+                        right_boundary=None, frac=None, auto_frac_factor=15.,
+                        delta=0.01, w=20, power=1. / 4,
+                        interpolate_before_increase=True):
+    """hic3defdr/util/lowess.py:95-244."""
+    return fit_many([(x, y, dict(
+        logx=logx, logy=logy, left_boundary=left_boundary,
+        right_boundary=right_boundary, frac=frac,
+        auto_frac_factor=auto_frac_factor, delta=delta, w=w, power=power,
+        interpolate_before_increase=interpolate_before_increase))],
+        weighted=True)[0]

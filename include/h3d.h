@@ -310,6 +310,15 @@ int h3d_lowess(const double* x, const double* y, int n, double frac, int it,
                double delta, double* y_fit, void* ws, size_t ws_bytes,
                h3d_stream_t stream);
 size_t h3d_lowess_ws_bytes(int n);
+/* n_jobs (<= 64) independent smoothing problems in one launch, one thread
+ * block each (the trends of all conditions, hic3defdr/analysis/analysis.py:
+ * 208-218): problem j is the slice [off_host[j], off_host[j] + n_host[j]) of
+ * the packed device arrays x / y / y_fit; off, n, frac, delta: HOST arrays. */
+int h3d_lowess_batch(const double* x, const double* y, const int* off_host,
+                     const int* n_host, const double* frac_host, int it,
+                     const double* delta_host, int n_jobs, double* y_fit,
+                     void* ws, size_t ws_bytes, h3d_stream_t stream);
+size_t h3d_lowess_batch_ws_bytes(int n_total, int n_jobs);
 
 /* disp[:, c] = disp_fn_c(dist) for integer distances: gather from a
  * (dist_max + 1, n_conds) table (hic3defdr/analysis/analysis.py:218). */
