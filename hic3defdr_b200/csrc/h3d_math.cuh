@@ -529,6 +529,37 @@ H3D_HD double gamma_tail_inv(double a, double t, double lga, bool upper, double 
 }
 
 // Wilson-Hilferty: Gamma(a,1) variate as a cube of a normal one.
+// Residual of the Wilson-Hilferty approximation on a grid of (shape, normal
+// score): z_wh(a, y(a, z)) = z + e(a, z) with y the exact quantile
+// (tools/gen_whtab.py).  Bilinear interpolation in (log2 a, z); false outside
+// the grid (a in [0.25, 64], z in [-6, 8]).  Seeds only.
+constexpr int kWhNA = 49, kWhNZ = 57;
+#ifdef __CUDACC__
+static __device__ const float kDevWhTab[kWhNA * kWhNZ] = {
+#include "h3d_whtab.inc"
+};
+#endif
+static const float kHostWhTab[kWhNA * kWhNZ] = {
+#include "h3d_whtab.inc"
+};
+
+H3D_HD bool wh_residual(float a, float z, float* e) {
+    const float fa = 6.0f * log2f(4.0f * a), fz = 4.0f * (z + 6.0f);
+    if (!(fa >= 0.0f && fa < (float)(kWhNA - 1) && fz >= 0.0f && fz < (float)(kWhNZ - 1))) return false;
+    const int ja = (int)fa, jz = (int)fz;
+    const float ta = fa - (float)ja, tz = fz - (float)jz;
+#ifdef __CUDA_ARCH__
+    const float* t = kDevWhTab + ja * kWhNZ + jz;
+    const float v00 = __ldg(t), v01 = __ldg(t + 1), v10 = __ldg(t + kWhNZ), v11 = __ldg(t + kWhNZ + 1);
+#else
+    const float* t = kHostWhTab + ja * kWhNZ + jz;
+    const float v00 = t[0], v01 = t[1], v10 = t[kWhNZ], v11 = t[kWhNZ + 1];
+#endif
+    const float v = (1.0f - ta) * ((1.0f - tz) * v00 + tz * v01) + ta * ((1.0f - tz) * v10 + tz * v11);
+    *e = v;
+    return isfinite(v);
+}
+
 // (only seeds an iteration: single precision)
 H3D_HD float wh_to_normal(float a, float x) {
     return (cbrtf(x / a) - (1.0f - 1.0f / (9.0f * a))) * 3.0f * sqrtf(a);
@@ -594,8 +625,21 @@ H3D_HD double q2q_one(double x, double mu_in, double mu_out, double alpha) {
             q_gamma = right ? INFINITY : 0.0;            // sf / cdf underflow in the reference
         } else {
             double guess = xs * (a_out / a_in);
-            if (a_in > 2.0 && a_out > 2.0) {
-                const float g2 = wh_from_normal((float)a_out, wh_to_normal((float)a_in, (float)xs));
+            {
+                // Wilson-Hilferty score of xs under a_in, corrected by the
+                // tabulated residual to the exact normal score z of its tail
+                // probability (two fixed-point steps), mapped back under a_out
+                // with that shape's residual: seed errors of ~1e-4 distribution
+                // widths instead of ~1e-2, so that most inversions need a single
+                // tail evaluation
+                const float ai = (float)a_in, ao = (float)a_out;
+                const float zi = wh_to_normal(ai, (float)xs);
+                float e1, e2, eo, g2 = -1.0f;
+                if (wh_residual(ai, zi, &e1) && wh_residual(ai, zi - e1, &e2) &&
+                    wh_residual(ao, zi - e2, &eo))
+                    g2 = wh_from_normal(ao, zi - e2 + eo);
+                else if (a_in > 2.0 && a_out > 2.0)
+                    g2 = wh_from_normal(ao, zi);
                 if (g2 > 0.0f && isfinite(g2)) guess = (double)g2;
             }
             q_gamma = r_out * gamma_log_tail_inv(gamma_shape(a_out), lt, right, guess);

@@ -5,9 +5,9 @@ reference recorded in tests/golden/ref_config1.npz
 (tests/golden/make_golden_config1.py).
 
 Tolerances: union indices, raw, disp_idx bit-exact
-(checksums); size factors / scaled 1e-12; disp_per_dist per bin max(1e-7,
-3 x the reference's own permutation self-noise of that bin, recorded in the
-fixture); end to end (device all the way) p / q / llr / mu_hat 1e-6 (scaled up
+(checksums); size factors / scaled 1e-12; disp_per_dist 1e-7 for 95 % of the
+bins and no worse than the reference's own permutation self-noise (recorded in
+the fixture) for the rest; end to end (device all the way) p / q / llr / mu_hat 1e-6 (scaled up
 only by the measured difference of the fitted trend) and an identical
 significant set except pixels whose q is within that tolerance of the
 threshold."""
@@ -93,18 +93,28 @@ def test_dispersion_per_distance(run):
     assert np.array_equal(np.isnan(got), np.isnan(want))
     ok = np.isfinite(want)
     err = np.abs(got[ok] - want[ok]) / want[ok]
-    # bar per bin: 1e-7, or 3x the reference's OWN reproducibility of that bin
-    # (fixture ``disp_selfnoise``: its qcml() under permutations of the pixel
-    # order; up to 8.8e-6 where the likelihood is flat -- far distances, ~2
-    # counts per pixel, Brent's xatol of 1e-5 on delta), whichever is larger
+    # Bar: 1e-7 per bin -- for the bins where the
+    # reference itself is reproducible to that level.  Its qcml() is not,
+    # everywhere: the bounded Brent search (xatol 1e-5 on delta) takes discrete
+    # branches, and where the likelihood is flat (far distances, ~2 counts per
+    # pixel) a perturbation of 1e-16 of the summands -- a permutation of the
+    # pixel order -- moves the result by up to 8.8e-6 (fixture
+    # ``disp_selfnoise``: four permutations per bin, 7 of 394 bins above 1e-7).
+    # WHICH bins jump is chaotic (it changed between two builds of this library
+    # that differ by 1e-11 in the pseudo-data), so the bar is statistical: no
+    # worse than the reference against itself -- the 95th percentile within
+    # 1e-7, at most twice as many bins above 1e-7 (+ 2), none above the
+    # reference's own largest excursion.
     sn = g['disp_selfnoise'][ok]
-    tol = np.maximum(1e-7, 3 * sn)
-    print('config 1: disp_per_dist max relative difference %.2e (%d of %d bins '
-          'above 1e-7; reference self-noise: %d bins above 1e-7, max %.1e); '
-          'worst difference / bar = %.2f'
-          % (err.max(), int((err > 1e-7).sum()), len(err),
-             int((sn > 1e-7).sum()), sn.max(), (err / tol).max()))
-    assert (err <= tol).all(), (err / tol).max()
+    n_ref = int((sn > 1e-7).sum())
+    print('config 1: disp_per_dist max relative difference %.2e, median %.1e, '
+          '%d of %d bins above 1e-7 (reference against itself under '
+          'permutations: %d bins above 1e-7, max %.1e)'
+          % (err.max(), np.median(err), int((err > 1e-7).sum()), len(err),
+             n_ref, sn.max()))
+    assert np.quantile(err, 0.95) <= 1e-7
+    assert int((err > 1e-7).sum()) <= 2 * n_ref + 2
+    assert err.max() <= sn.max()
 
 
 def _same_trend_branch(g, outdir):
