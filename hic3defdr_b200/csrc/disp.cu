@@ -402,18 +402,25 @@ nll_kernel(const double* __restrict__ pseudo, long long ld, const int* __restric
     const double* __restrict__ base = pseudo + (long long)cr.pseudo_row[c] * ld;
     FixAcc a = {0ll, 0ll, 0};
     if (r >= 10.0) {
-        for (long long i = lo + threadIdx.x; i < hi; i += 256) {
-            double z = 0.0, t = 0.0;
-#pragma unroll
-            for (int k = 0; k < MAXRC; ++k) {
-                if (k < nr) {
-                    const double y = base[(long long)k * ld + i];
-                    z += y;
-                    t += stirling_core(y + r);
-                }
-            }
-            fix_add(a, (t + cst) - stirling_core(z + nrr));
+        // every argument is >= r: the number of Stirling correction terms is
+        // uniform over the block (h3d_math.cuh, stirling_core_nt)
+#define H3D_NLL_LOOP(NT)                                                        \
+        for (long long i = lo + threadIdx.x; i < hi; i += 256) {                \
+            double z = 0.0, t = 0.0;                                            \
+            _Pragma("unroll")                                                   \
+            for (int k = 0; k < MAXRC; ++k) {                                   \
+                if (k < nr) {                                                   \
+                    const double y = base[(long long)k * ld + i];               \
+                    z += y;                                                     \
+                    t += stirling_core_nt<NT>(y + r);                           \
+                }                                                               \
+            }                                                                   \
+            fix_add(a, (t + cst) - stirling_core_nt<NT>(z + nrr));              \
         }
+        if (r >= 40.0) { H3D_NLL_LOOP(4) }
+        else if (r >= 20.0) { H3D_NLL_LOOP(5) }
+        else { H3D_NLL_LOOP(7) }
+#undef H3D_NLL_LOOP
     } else {
         // uniform shift of every argument by n_shift units (see stirling_core_shifted);
         // the "- n" terms of the (R_c + 1) shifted log-gammas leave (R_c - 1) n_shift

@@ -671,25 +671,31 @@ H3D_HD double stirling_corr(double x) {
 
 // Stirling's series term of one log-gamma argument x >= 10 without the
 // "- x + .5 ln 2pi" part (which cancels or is constant in the conditional
-// likelihood): (x - .5) ln x + corr(x), table-driven log, refined-seed reciprocal
-H3D_HD double stirling_core(double x) {
+// likelihood): (x - .5) ln x + corr(x), table-driven log, refined-seed
+// reciprocal.  NT = number of terms of the correction series that the smallest
+// argument of the evaluation calls for (truncation below 1e-17): 4 for
+// x >= 40 (next term 1 / (1188 x^9) = 3e-18), 5 for x >= 20, 7 for x >= 10.
+template <int NT>
+H3D_HD double stirling_core_nt(double x) {
+    static_assert(NT == 4 || NT == 5 || NT == 7, "4, 5 or 7 terms");
     const double ix = fast_rcp_pos(x);
     const double ix2 = ix * ix;
 #ifdef __CUDA_ARCH__
-    double c = fma(ix2, kDevStirling[6], kDevStirling[5]);
-    c = fma(ix2, c, kDevStirling[4]);
-    c = fma(ix2, c, kDevStirling[3]);
-    c = fma(ix2, c, kDevStirling[2]);
-    c = fma(ix2, c, kDevStirling[1]);
-    c = fma(ix2, c, kDevStirling[0]);
+    double c = kDevStirling[NT - 1];
+#pragma unroll
+    for (int k = NT - 2; k >= 0; --k) c = fma(ix2, c, kDevStirling[k]);
     const double corr = ix * c;
 #else
-    const double corr = ix * (1.0 / 12.0 + ix2 * (-1.0 / 360.0 + ix2 * (1.0 / 1260.0 +
-        ix2 * (-1.0 / 1680.0 + ix2 * (1.0 / 1188.0 + ix2 * (-691.0 / 360360.0 +
-        ix2 * (1.0 / 156.0)))))));
+    const double cf[7] = {1.0 / 12.0, -1.0 / 360.0, 1.0 / 1260.0, -1.0 / 1680.0, 1.0 / 1188.0,
+                          -691.0 / 360360.0, 1.0 / 156.0};
+    double c = cf[NT - 1];
+    for (int k = NT - 2; k >= 0; --k) c = fma(ix2, c, cf[k]);
+    const double corr = ix * c;
 #endif
     return fma(x - 0.5, fast_log_pos(x), corr);
 }
+
+H3D_HD double stirling_core(double x) { return stirling_core_nt<7>(x); }
 
 // the same for arguments that may be below 10: ALL arguments of a likelihood
 // evaluation are shifted up by the same n = ceil(10 - r) >= 1 unit steps (r > 0
