@@ -280,6 +280,58 @@ def owner_layout(all_counts, per, me):
     return n_recv, shift, runs
 
 
+def lpt_layout(all_counts, me, weight=None):
+    """Ownership and buffer layout of the peer-memory pooling when the owners
+    are chosen AFTER the per-(rank, distance) pixel counts are known
+    (``all_counts``: (ws, n_dist), every rank's local pooled order is plain
+    distance order).  Distances are dealt to ranks by longest-processing-time
+    on ``weight`` (default: the genome-wide pixel count of the distance;
+    distances without pixels weigh nothing), identically on every rank.  The
+    buffer of owner k holds its owned distances in increasing order, inside a
+    distance one run per source rank in rank order -- i.e. every owned distance
+    is one contiguous segment.
+    Returns dict(owner (n_dist,), owned (list of arrays per rank), shift
+    (n_dist,) for THIS rank: pooled position + shift = position in the owner's
+    buffer, seg_start (n_owned + 1,) of THIS rank's buffer, n_recv (ws,))."""
+    c = np.asarray(all_counts, dtype=np.int64)
+    ws, n_dist = c.shape
+    tot = c.sum(axis=0)
+    w = tot.astype(float) if weight is None else np.asarray(weight, float)
+    owner = np.asarray(lpt_assign([float(v) for v in w], ws), dtype=np.int64)
+    # distances without pixels: spread them, they cost nothing
+    owned = [np.flatnonzero(owner == k) for k in range(ws)]
+    shift = np.zeros(n_dist, dtype=np.int64)
+    local_start = np.cumsum(c[me]) - c[me]
+    n_recv = np.zeros(ws, dtype=np.int64)
+    seg_start = None
+    for k in range(ws):
+        d = owned[k]
+        seg = np.concatenate([[0], np.cumsum(tot[d])]).astype(np.int64)
+        n_recv[k] = seg[-1]
+        before_me = c[:me][:, d].sum(axis=0)             # lower ranks' share
+        shift[d] = seg[:-1] + before_me - local_start[d]
+        if k == me:
+            seg_start = seg
+    return dict(owner=owner, owned=owned, shift=shift, seg_start=seg_start,
+                n_recv=n_recv)
+
+
+def merge_disp_owned(disp_owned, owned, n_dist):
+    """``disp_owned``: (len(owned[me]), C) results of this rank's distances;
+    ``owned``: every rank's distance list (``lpt_layout``).  Returns the full
+    (n_dist, C) table on every rank."""
+    ws, me = world_size(), rank()
+    n_conds = disp_owned.shape[1]
+    cap = max(1, max(len(d) for d in owned))
+    pad = np.full((cap, n_conds), np.nan)
+    pad[:len(owned[me])] = disp_owned[:len(owned[me])]
+    out = _all_gather_flat(_coll_tensor(pad)).cpu().numpy()
+    full = np.full((n_dist, n_conds), np.nan)
+    for k in range(ws):
+        full[owned[k]] = out[k][:len(owned[k])]
+    return full
+
+
 class RawMatrix(object):
     """a (rows, ld) float64 matrix in device memory that torch did not
     allocate (a peer-shared receive buffer): just what the C-ABI calls need"""

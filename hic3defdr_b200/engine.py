@@ -266,29 +266,32 @@ def pool_by_distance(states, dist_max, n_reps=None):
 def pool_to_owners(states, dist_max, n_reps):
     """``pool_by_distance`` + the exchange by distance owner in one pass over
     the pixels (multi-GPU, NCCL, one node): after the local stable rank by
-    (owner, distance) and ONE all-gather of the per-(rank, distance) counts,
-    the pooling gather writes every pixel's counts and factors straight into
-    the buffer of the rank that owns its distance, over NVLink (csrc/peer.cu).
-    Returns (x, f, dist_cat, runs, offs, n_owned) with x, f the two halves of
-    this rank's receive buffer."""
+    distance and ONE all-gather of the per-(rank, distance) counts, the owners
+    are dealt by longest-processing-time on the genome-wide pixel counts
+    (``dist.lpt_layout``) and the pooling gather writes every pixel's counts
+    and factors straight into the buffer of the rank that owns its distance,
+    over NVLink (csrc/peer.cu).  Returns (x, f, dist_cat, seg_start, offs,
+    layout) with x, f the two halves of this rank's receive buffer and
+    seg_start the boundaries of its owned distances."""
     ws, me = hdist.world_size(), hdist.rank()
-    counts, offs, dist_cat, rank, key_start, key_of_dist, per = \
-        _pool_local_order(states, dist_max)
-    seg_start = ops.to_host(key_start)
+    n_dist = dist_max + 1
+    with hdist.single_process():         # local order: plain distance keys
+        counts, offs, dist_cat, rank, key_start, key_of_dist, per = \
+            _pool_local_order(states, dist_max)
     # the collective also orders the ranks: nobody writes into a buffer whose
     # previous contents are still being read (stream order on every rank)
-    all_counts = hdist._all_gather_counts(np.diff(seg_start))
-    n_recv, shift, runs = hdist.owner_layout(all_counts, per, me)
-    ld = (int(n_recv.max()) + 255) // 256 * 256 + 256
+    all_counts = hdist._all_gather_flat(
+        (key_start[1:] - key_start[:-1]).contiguous()).cpu().numpy()
+    lay = hdist.lpt_layout(all_counts, me)
+    ld = (int(lay['n_recv'].max()) + 255) // 256 * 256 + 256
     ptrs = hdist._PEERS.ensure(2 * n_reps * ld * 8)
-    owner_of_key = np.arange(per * ws) // per
     _pool_gather(states, counts, offs, rank, key_start, key_of_dist, per,
-                 n_reps, owner_of_key, shift, ptrs, ld)
+                 n_reps, lay['owner'], lay['shift'], ptrs, ld)
     hdist.fence_peer_writes()
     own = ptrs[me]
     x = hdist.RawMatrix(own, (n_reps, ld))
     f = hdist.RawMatrix(own + n_reps * ld * 8, (n_reps, ld))
-    return x, f, dist_cat, runs, offs, per
+    return x, f, dist_cat, lay['seg_start'], offs, lay
 
 
 def fit_trends(disp_per_dist, dist_max, cond_names, frac=None,
@@ -358,9 +361,23 @@ def estimate_disp(states, design, dist_max, cond_names=None, estimator='qcml',
     if hdist.peer_exchange_enabled() and not callable(estimator):
         # multi-GPU: the pooling gather writes into the owners' buffers
         with stage('estimate_disp/pool'):
-            x, f, dist_cat, runs, offs, n_owned = pool_to_owners(
+            x, f, dist_cat, seg_own, offs, lay = pool_to_owners(
                 states, dist_max, design.shape[0])
         n_tot = int(offs[-1])
+        with stage('estimate_disp/qcml'):
+            if len(seg_own) > 1:
+                disp_own, stats = ops.estimate_dispersion(
+                    x, f, seg_own, design, estimator)
+            else:
+                disp_own, stats = np.zeros((0, n_conds)), None
+        with stage('estimate_disp/merge'):
+            disp_per_dist = hdist.merge_disp_owned(disp_own, lay['owned'],
+                                                   dist_max + 1)
+        if stats is None:
+            stats = dict(outer_iterations=0, nll_evaluations=0,
+                         pixel_equalizations=0, launches=0,
+                         equalize_launches=0, equalize_us=0, nll_launches=0,
+                         nll_us=0, capped_segments=0)
     else:
         with stage('estimate_disp/pool'):
             x, f, dist_cat, seg_start, offs = pool_by_distance(
@@ -371,15 +388,16 @@ def estimate_disp(states, design, dist_max, cond_names=None, estimator='qcml',
         with stage('estimate_disp/exchange'):
             x, f, runs = hdist.exchange_by_distance(x, f, seg_start, n_tot)
         n_owned = n_keys // hdist.world_size()
-    with stage('estimate_disp/qcml'):
-        if callable(estimator):
-            disp_per_dist, stats = _estimate_with_callable(
-                x, f, runs, n_owned, design, estimator)
-        else:
-            disp_per_dist, stats = ops.estimate_dispersion(
-                x, f, n_owned, design, estimator, runs=runs)
-    with stage('estimate_disp/merge'):
-        disp_per_dist = hdist.merge_disp_per_dist(disp_per_dist, dist_max + 1)
+        with stage('estimate_disp/qcml'):
+            if callable(estimator):
+                disp_per_dist, stats = _estimate_with_callable(
+                    x, f, runs, n_owned, design, estimator)
+            else:
+                disp_per_dist, stats = ops.estimate_dispersion(
+                    x, f, n_owned, design, estimator, runs=runs)
+        with stage('estimate_disp/merge'):
+            disp_per_dist = hdist.merge_disp_per_dist(disp_per_dist,
+                                                      dist_max + 1)
     del x, f
     with stage('estimate_disp/trend'):
         fns, table = fit_trends(disp_per_dist, dist_max, cond_names, frac,

@@ -344,3 +344,37 @@ def test_bh_sample_positions_stay_in_range():
         sel = hd.sample_positions(n, take).numpy()
         assert sel[0] == 0 and sel[-1] == n - 1
         assert (np.diff(sel) >= 0).all() and len(sel) == take
+
+
+def test_lpt_layout_tiles_every_owner_buffer():
+    """dist.lpt_layout (ownership chosen after the counts are known): the
+    slices every source rank writes tile every owner's buffer exactly, every
+    owned distance is one contiguous segment (sources in rank order), empty
+    distances weigh nothing, and the deal balances the pixel counts."""
+    from hic3defdr_b200 import dist as hd
+    rng = np.random.default_rng(3)
+    ws, n_dist = 5, 61
+    counts = rng.integers(0, 400, size=(ws, n_dist)) * \
+        np.linspace(2.0, 0.5, n_dist).astype(int).clip(1)
+    counts[:, :4] = 0                          # below dist_thresh_min: no pixels
+    lays = [hd.lpt_layout(counts, me) for me in range(ws)]
+    owner = lays[0]['owner']
+    for lay in lays:
+        assert np.array_equal(lay['owner'], owner)
+    for k in range(ws):
+        d_own = lays[k]['owned'][k]
+        assert (np.diff(d_own) > 0).all() and (owner[d_own] == k).all()
+        seg = lays[k]['seg_start']
+        assert np.array_equal(np.diff(seg), counts[:, d_own].sum(axis=0))
+        cover = np.zeros(int(lays[k]['n_recv'][k]), dtype=int)
+        for me in range(ws):
+            local_start = np.cumsum(counts[me]) - counts[me]
+            last_hi = {}
+            for j, d in enumerate(d_own):
+                lo = local_start[d] + lays[me]['shift'][d]
+                hi = lo + counts[me, d]
+                assert seg[j] <= lo and hi <= seg[j + 1]
+                cover[lo:hi] += 1
+        assert (cover == 1).all()
+    loads = np.array([counts[:, lays[0]['owned'][k]].sum() for k in range(ws)])
+    assert (loads.max() - loads.min()) / loads.mean() < 0.05
