@@ -603,7 +603,7 @@ def main():
     if not args.no_e2e:
         step_e2e()
         step_e2e()
-        if os.environ.get('H3D_E2E_TIMELINE') and rank == 0:
+        if os.environ.get('H3D_E2E_TIMELINE') and world == 1:   # one process only: the extra step would leave the other ranks' collectives unmatched
             # where the overlapped host-buffer step spends its time: CUDA event
             # pairs around the stages on the compute stream (no synchronisation)
             trace.record_events(True)

@@ -426,14 +426,74 @@ def _peer_copy(src, src_off, ptrs, dst_off, nbytes):
                    ptr(nb), k1 - k0, torch.cuda.current_stream().cuda_stream)
 
 
+_PEER_OK = {}
+
+
+def _probe_peer_memory():
+    """One collective probe per process group: every rank allocates a small
+    buffer, shares its CUDA IPC handle and opens everybody else's.  Peer
+    memory is used only if that worked on EVERY rank (e.g. not across nodes,
+    not where IPC is disabled); otherwise the NCCL transfers are."""
+    import ctypes
+    from hic3defdr_b200._native import lib
+    ok, own, opened, why = 1, ctypes.c_void_p(), [], ''
+    mine = None
+    try:
+        handle = (ctypes.c_ubyte * 64)()
+        lib().call('h3d_peer_alloc', 4096, ctypes.byref(own), handle)
+        mine = bytes(handle)
+    except Exception as e:                       # noqa: BLE001
+        ok, why = 0, str(e)
+    handles = [None] * world_size()
+    td.all_gather_object(handles, mine)          # every rank takes part
+    if ok and all(h is not None for h in handles):
+        try:
+            for k, h in enumerate(handles):
+                if k == rank():
+                    continue
+                p = ctypes.c_void_p()
+                lib().call('h3d_peer_open',
+                           (ctypes.c_ubyte * 64).from_buffer_copy(h),
+                           ctypes.byref(p))
+                opened.append(p.value)
+        except Exception as e:                   # noqa: BLE001
+            ok, why = 0, str(e)
+    else:
+        ok = 0
+    if not ok:
+        import sys
+        print('hic3defdr_b200: CUDA IPC peer memory unavailable (%s); using '
+              'NCCL transfers for the exchanges' % why, file=sys.stderr)
+    t = torch.tensor([ok], dtype=torch.int32, device='cuda')
+    td.all_reduce(t, op=td.ReduceOp.MIN)
+    for p in opened:
+        try:
+            lib().call('h3d_peer_close', p)
+        except Exception:                        # noqa: BLE001
+            pass
+    barrier()
+    if own.value:
+        try:
+            lib().call('h3d_peer_free', own.value)
+        except Exception:                        # noqa: BLE001
+            pass
+    return bool(int(t.item()))
+
+
 def peer_exchange_enabled():
     """The pooling gather writes straight into the owners' buffers over
-    NVLink (csrc/peer.cu) when the ranks run NCCL on one node; ``H3D_EXCHANGE=
+    NVLink (csrc/peer.cu) when the ranks run NCCL on one node and CUDA IPC
+    works between all of them (probed once, collectively); ``H3D_EXCHANGE=
     nccl`` selects the grouped point-to-point transfers instead."""
     import os
-    return initialized() and world_size() > 1 and \
-        td.get_backend() == 'nccl' and \
-        os.environ.get('H3D_EXCHANGE', 'peer') == 'peer'
+    if not (initialized() and world_size() > 1 and
+            td.get_backend() == 'nccl' and
+            os.environ.get('H3D_EXCHANGE', 'peer') == 'peer'):
+        return False
+    key = world_size()
+    if key not in _PEER_OK:
+        _PEER_OK[key] = _probe_peer_memory()
+    return _PEER_OK[key]
 
 
 def fence_peer_writes():
