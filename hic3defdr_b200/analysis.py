@@ -21,6 +21,8 @@ Differences a caller can observe (all documented in DESIGN.md):
     range instead and the ranks write their slices of the same ``.npy`` files
     (outdir must be on a file system all ranks share, as on one node).
 """
+import collections
+import itertools
 import json
 import os
 import sys
@@ -35,7 +37,7 @@ import torch
 
 from hic3defdr_b200 import dist as hdist
 from hic3defdr_b200 import clusters as hclusters
-from hic3defdr_b200 import engine, ops, staging
+from hic3defdr_b200 import engine, hostio, ops, staging
 
 
 def eprint(*args, **kwargs):
@@ -368,24 +370,58 @@ class HiC3DeFDR(object):
         if self._writer is not None:
             self._writer.wait()
 
+    def _submit_inputs(self, pool, chrom):
+        """Queues the host side of ``prepare_data`` for one chromosome on
+        ``pool``, one job per file (bias text parse, npz inflate -- zlib
+        releases the GIL -- and the loop cluster files); returns a function
+        that waits for them and gives (bias_raw, mats, loop_pixels)."""
+        bias = [pool.submit(_loadtxt, p.replace('<chrom>', chrom))
+                for p in self.bias_patterns]
+        mats = [pool.submit(
+            lambda p: hostio.load_npz(p).tocsr(), p.replace('<chrom>', chrom))
+            for p in self.raw_npz_patterns]
+        loops = [pool.submit(load_clusters, pattern.replace('<chrom>', chrom))
+                 for pattern in self.loop_patterns.values()] \
+            if self.loop_patterns else None
+
+        def collect():
+            bias_raw = np.ascontiguousarray(
+                np.array([f.result() for f in bias]).T)
+            loop_pixels = None
+            if loops is not None:
+                loop_pixels = set().union(
+                    *sum((f.result() for f in loops), []))
+            return bias_raw, [f.result() for f in mats], loop_pixels
+        return collect
+
     def _load_inputs(self, chrom, n_threads=-1):
         """Host side of ``prepare_data`` for one chromosome: bias vectors,
         replicate matrices (each npz inflated once, in parallel) and loop
-        pixels.  Thread-safe: ``prepare_data()`` runs it for the next
-        chromosome while the GPU works on the current one."""
-        bias_raw = np.ascontiguousarray(np.array(
-            [_loadtxt(p.replace('<chrom>', chrom))
-             for p in self.bias_patterns]).T)
-        with ThreadPoolExecutor(self._io_threads(n_threads)) as ex:
-            mats = list(ex.map(
-                lambda p: sparse.load_npz(p.replace('<chrom>', chrom)).tocsr(),
-                self.raw_npz_patterns))
-        loop_pixels = None
-        if self.loop_patterns:
-            loop_pixels = set().union(
-                *sum((load_clusters(pattern.replace('<chrom>', chrom))
-                      for pattern in self.loop_patterns.values()), []))
-        return bias_raw, mats, loop_pixels
+        pixels."""
+        with ThreadPoolExecutor(self._io_threads(n_threads)) as pool:
+            return self._submit_inputs(pool, chrom)()
+
+    def _prefetched_inputs(self, chroms, n_threads=-1):
+        """Yields (chrom, inputs) in order while the files of the following
+        chromosomes are read on a shared pool of I/O threads: as many
+        chromosomes in flight as the threads can serve at one file each
+        (with the arithmetic on the GPU the
+        inflate of the input files is the critical path of a run)."""
+        n_io = self._io_threads(n_threads)
+        depth = max(1, n_io // max(1, len(self.raw_npz_patterns)))
+        with ThreadPoolExecutor(n_io) as pool:
+            todo = iter(chroms)
+            queue = collections.deque(
+                (c, self._submit_inputs(pool, c))
+                for c in itertools.islice(todo, depth))
+            while queue:
+                c, collect = queue.popleft()
+                inputs = collect()
+                nxt = next(todo, None)
+                if nxt is not None:
+                    queue.append((nxt, self._submit_inputs(pool, nxt)))
+                yield c, inputs
+                del inputs
 
     def _chrom_state(self, chrom, names):
         """device tensors of one chromosome, from the cache or from disk."""
@@ -432,24 +468,17 @@ class HiC3DeFDR(object):
         if norm not in ops.NORMS:
             raise KeyError(norm)
         if chrom is None:
-            # the next chromosome's files are read (npz inflate, text parse)
-            # while this one is on the GPU, and this one's outputs are written
-            # while the next one is computed
+            # the following chromosomes' files are read (npz inflate, text
+            # parse) while this one is on the GPU, and this one's outputs are
+            # written while the next ones are computed
             chroms = self._my_chroms()
             defer, self._defer_writes = self._defer_writes, True
             try:
-                with ThreadPoolExecutor(1) as loader:
-                    nxt = loader.submit(self._load_inputs, chroms[0],
-                                        n_threads) if chroms else None
-                    for i, c in enumerate(chroms):
-                        inputs = nxt.result()
-                        nxt = loader.submit(self._load_inputs, chroms[i + 1],
-                                            n_threads) \
-                            if i + 1 < len(chroms) else None
-                        self.prepare_data(chrom=c, norm=norm, n_bins=n_bins,
-                                          n_threads=n_threads, verbose=False,
-                                          _inputs=inputs)
-                        del inputs
+                for c, inputs in self._prefetched_inputs(chroms, n_threads):
+                    self.prepare_data(chrom=c, norm=norm, n_bins=n_bins,
+                                      n_threads=n_threads, verbose=False,
+                                      _inputs=inputs)
+                    del inputs
             finally:
                 self._defer_writes = defer
             if not defer:

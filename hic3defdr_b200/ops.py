@@ -5,6 +5,7 @@ be numpy arrays (copied to the current CUDA device) or CUDA torch tensors;
 outputs are CUDA torch tensors unless stated.  No CPU fallback.
 """
 import ctypes
+import warnings
 
 import numpy as np
 import torch
@@ -32,7 +33,14 @@ def dev(a, dtype=None):
         a = np.ascontiguousarray(a)
         if a.dtype == np.bool_:
             a = a.view(np.uint8)
-        t = torch.from_numpy(a)
+        if a.flags.writeable:
+            t = torch.from_numpy(a)
+        else:
+            # views of inflated file buffers (hostio.load_npz) are read-only;
+            # the tensor is only ever the source of the upload below
+            with warnings.catch_warnings():
+                warnings.simplefilter('ignore', UserWarning)
+                t = torch.from_numpy(a)
     if dtype is not None and t.dtype != dtype:
         t = t.to(dtype)
     return t.cuda().contiguous()

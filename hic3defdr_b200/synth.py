@@ -110,39 +110,64 @@ def make_chrom(n, n_reps, dist_max, seed, amp=300.0, res_scale=1.0, pad=5,
     return mats, bias, clusters
 
 
+def _write_chrom(task):
+    """one chromosome of ``write_dataset`` (a top-level function: it also runs
+    in forked worker processes); returns whether cluster files were written."""
+    (root, rep_names, ci, chrom, n, n_reps, dist_max, config, amp, res_scale,
+     loops, dtype) = task
+    seed = BASE_SEED + 1000 * config + 100 * ci
+    mats, bias, clusters, classes = make_chrom(
+        n, n_reps, dist_max, seed, amp=amp, res_scale=res_scale,
+        loops=loops, dtype=dtype, return_classes=True)
+    for r, rep in enumerate(rep_names):
+        sparse.save_npz(os.path.join(root, rep, '%s_raw.npz' % chrom), mats[r])
+        np.savetxt(os.path.join(root, rep, '%s_kr.bias' % chrom), bias[:, r])
+    if clusters is None:
+        return False
+    import json
+    with open(os.path.join(root, 'clusters', 'loops_%s.json' % chrom),
+              'w') as h:
+        json.dump([[list(p) for p in c] for c in clusters], h)
+    # ground truth in the format of the reference's simulate()
+    # (analysis/simulation.py:141: one label per cluster)
+    np.savetxt(os.path.join(root, 'clusters', 'labels_%s.txt' % chrom),
+               classes, fmt='%s')
+    return True
+
+
 def write_dataset(root, chrom_sizes, n_reps=4, dist_max=200, config=1,
-                  amp=300.0, res_scale=1.0, loops=False, dtype=np.int64):
+                  amp=300.0, res_scale=1.0, loops=False, dtype=np.int64,
+                  n_jobs=1):
     """Writes a dataset under ``root`` and returns the kwargs for HiC3DeFDR
-    (raw_npz_patterns, bias_patterns, chroms, design)."""
+    (raw_npz_patterns, bias_patterns, chroms, design).  ``n_jobs`` > 1
+    generates the chromosomes in that many forked processes (same files: the
+    random streams are per chromosome and replicate); fork before the process
+    has initialised CUDA."""
     import pandas as pd
     rep_names = ['A%d' % (i + 1) for i in range(n_reps // 2)] + \
         ['B%d' % (i + 1) for i in range(n_reps - n_reps // 2)]
     for rep in rep_names:
         os.makedirs(os.path.join(root, rep), exist_ok=True)
+    if loops:
+        os.makedirs(os.path.join(root, 'clusters'), exist_ok=True)
+    tasks = [(root, rep_names, ci, chrom, n, n_reps, dist_max, config, amp,
+              res_scale, loops, dtype)
+             for ci, (chrom, n) in enumerate(chrom_sizes.items())]
+    if n_jobs > 1 and len(tasks) > 1:
+        import multiprocessing
+        # largest chromosomes first: the pool drains evenly
+        order = sorted(range(len(tasks)), key=lambda i: -tasks[i][4])
+        with multiprocessing.get_context('fork').Pool(
+                min(n_jobs, len(tasks))) as pool:
+            wrote = pool.map(_write_chrom, [tasks[i] for i in order],
+                             chunksize=1)
+    else:
+        wrote = [_write_chrom(t) for t in tasks]
     loop_patterns = None
-    for ci, (chrom, n) in enumerate(chrom_sizes.items()):
-        seed = BASE_SEED + 1000 * config + 100 * ci
-        mats, bias, clusters, classes = make_chrom(
-            n, n_reps, dist_max, seed, amp=amp, res_scale=res_scale,
-            loops=loops, dtype=dtype, return_classes=True)
-        for r, rep in enumerate(rep_names):
-            sparse.save_npz(os.path.join(root, rep, '%s_raw.npz' % chrom),
-                            mats[r])
-            np.savetxt(os.path.join(root, rep, '%s_kr.bias' % chrom),
-                       bias[:, r])
-        if clusters is not None:
-            import json
-            os.makedirs(os.path.join(root, 'clusters'), exist_ok=True)
-            with open(os.path.join(root, 'clusters', 'loops_%s.json' % chrom),
-                      'w') as h:
-                json.dump([[list(p) for p in c] for c in clusters], h)
-            # ground truth in the format of the reference's simulate()
-            # (analysis/simulation.py:141: one label per cluster)
-            np.savetxt(os.path.join(root, 'clusters', 'labels_%s.txt' % chrom),
-                       classes, fmt='%s')
-            loop_patterns = {
-                'A': os.path.join(root, 'clusters', 'loops_<chrom>.json'),
-                'B': os.path.join(root, 'clusters', 'loops_<chrom>.json')}
+    if any(wrote):
+        loop_patterns = {
+            'A': os.path.join(root, 'clusters', 'loops_<chrom>.json'),
+            'B': os.path.join(root, 'clusters', 'loops_<chrom>.json')}
     design = pd.DataFrame(
         {'A': [r.startswith('A') for r in rep_names],
          'B': [r.startswith('B') for r in rep_names]}, index=rep_names)

@@ -30,3 +30,47 @@ def test_writer_round_trip_and_error_propagation(tmp_path):
     w.submit(arrays['b'], str(tmp_path / 'again.npy'))   # usable afterwards
     w.wait()
     assert os.path.exists(str(tmp_path / 'again.npy'))
+
+
+def _small_inputs(root, chroms, n_reps=4, loops=False):
+    from hic3defdr_b200.synth import write_dataset
+    return write_dataset(str(root), {c: 60 + 7 * i for i, c in enumerate(chroms)},
+                         n_reps=n_reps, dist_max=20, config=7, loops=loops)
+
+
+@pytest.mark.parametrize('n_threads,loops', [(-1, False), (0, True), (3, True)])
+def test_prefetched_inputs_match_the_plain_loader(tmp_path, n_threads, loops):
+    """The look-ahead loader of ``prepare_data`` (several chromosomes in flight
+    on one pool) yields every chromosome once, in order, with the inputs the
+    one-chromosome loader gives (reference: analysis/analysis.py:84-101 reads
+    the same files one by one)."""
+    from hic3defdr_b200 import HiC3DeFDR
+    chroms = ['chr%d' % i for i in range(1, 8)]
+    kw = _small_inputs(tmp_path / 'in', chroms, loops=loops)
+    if not loops:
+        kw.pop('loop_patterns')
+    h = HiC3DeFDR(outdir=str(tmp_path / 'out'), dist_thresh_max=20, **kw)
+    seen = []
+    for c, (bias, mats, loop_pixels) in h._prefetched_inputs(chroms, n_threads):
+        seen.append(c)
+        wb, wm, wl = h._load_inputs(c, 0)
+        assert np.array_equal(bias, wb) and bias.flags.c_contiguous
+        assert len(mats) == len(wm) == 4
+        for a, b in zip(mats, wm):
+            assert a.format == 'csr' and (a != b).nnz == 0 and a.dtype == b.dtype
+        assert loop_pixels == wl and (loop_pixels is not None) == loops
+    assert seen == chroms
+    assert list(h._prefetched_inputs([], n_threads)) == []
+
+
+def test_prefetched_inputs_surface_a_missing_file(tmp_path):
+    from hic3defdr_b200 import HiC3DeFDR
+    chroms = ['chr1', 'chr2', 'chr3']
+    kw = _small_inputs(tmp_path / 'in', chroms)
+    kw.pop('loop_patterns')
+    os.remove(kw['raw_npz_patterns'][1].replace('<chrom>', 'chr2'))
+    h = HiC3DeFDR(outdir=str(tmp_path / 'out'), dist_thresh_max=20, **kw)
+    it = h._prefetched_inputs(chroms, -1)
+    assert next(it)[0] == 'chr1'
+    with pytest.raises(OSError):
+        next(it)
