@@ -76,22 +76,84 @@ class _AsyncWriter(object):
     file while the main thread goes on with the next chromosome.  ``wait``
     blocks until every file is on disk and re-raises the first failure."""
 
-    def __init__(self, n_threads):
+    # device tensors go through two pinned staging buffers per writer thread,
+    # CHUNK bytes at a time: the copy of a chunk (PCIe rate, no page faults of
+    # a fresh host allocation) overlaps the write() of the previous one, and
+    # the pinned footprint stays bounded whatever the array sizes
+    CHUNK = 16 << 20
+
+    def __init__(self, n_threads, staged=None):
         self.pool = ThreadPoolExecutor(max(1, n_threads))
         self.futures = []
         self.streams = {}
+        self.staging = {}
         self.lock = threading.Lock()
+        self.staged = (os.environ.get('H3D_WRITER', 'staged') == 'staged') \
+            if staged is None else staged
+
+    def _thread_stream(self):
+        key = threading.get_ident()
+        with self.lock:
+            stream = self.streams.get(key)
+            if stream is None:
+                stream = self.streams[key] = torch.cuda.Stream()
+        return stream
+
+    def _thread_staging(self):
+        key = threading.get_ident()
+        with self.lock:
+            st = self.staging.get(key)
+        if st is None:
+            st = [(torch.empty(self.CHUNK, dtype=torch.uint8, pin_memory=True),
+                   torch.cuda.Event()) for _ in range(2)]
+            with self.lock:
+                self.staging[key] = st
+        return st
+
+    @staticmethod
+    def write_npy_chunks(path, dtype, shape, chunks):
+        """``np.save(path, a)`` of a C-ordered array given as an iterable of
+        buffers holding its bytes in order (same file, byte for byte)."""
+        with open(path, 'wb') as handle:
+            np.lib.format.write_array_header_1_0(handle, {
+                'descr': np.lib.format.dtype_to_descr(np.dtype(dtype)),
+                'fortran_order': False, 'shape': tuple(int(v) for v in shape)})
+            for c in chunks:
+                handle.write(c)
+
+    def _device_chunks(self, flat, stream):
+        """the bytes of a contiguous device tensor, CHUNK at a time, through
+        the calling thread's staging buffers (views: valid until the next
+        item is asked for)."""
+        staging = self._thread_staging()
+        n, off, k, pending = flat.numel(), 0, 0, []
+        while off < n or pending:
+            if off < n and len(pending) < 2:
+                m = min(self.CHUNK, n - off)
+                buf, ev = staging[k % 2]
+                with torch.cuda.stream(stream):
+                    buf[:m].copy_(flat[off:off + m], non_blocking=True)
+                    ev.record(stream)
+                pending.append((buf, m, ev))
+                off += m
+                k += 1
+                continue
+            buf, m, ev = pending.pop(0)
+            ev.synchronize()
+            yield memoryview(buf.numpy())[:m]
 
     def _job(self, data, path, event, device):
         if isinstance(data, torch.Tensor):
             if data.is_cuda:
                 torch.cuda.set_device(device)
-                key = threading.get_ident()
-                with self.lock:
-                    stream = self.streams.get(key)
-                    if stream is None:
-                        stream = self.streams[key] = torch.cuda.Stream()
+                stream = self._thread_stream()
                 stream.wait_event(event)
+                if self.staged and data.is_contiguous():
+                    np_dtype = torch.empty(0, dtype=data.dtype).numpy().dtype
+                    flat = data.reshape(-1).view(torch.uint8)
+                    self.write_npy_chunks(path, np_dtype, data.shape,
+                                          self._device_chunks(flat, stream))
+                    return
                 with torch.cuda.stream(stream):
                     host = data.to('cpu', non_blocking=False)
                 stream.synchronize()

@@ -137,12 +137,13 @@ def _write_chrom(task):
 
 def write_dataset(root, chrom_sizes, n_reps=4, dist_max=200, config=1,
                   amp=300.0, res_scale=1.0, loops=False, dtype=np.int64,
-                  n_jobs=1):
+                  n_jobs=1, generate=True):
     """Writes a dataset under ``root`` and returns the kwargs for HiC3DeFDR
     (raw_npz_patterns, bias_patterns, chroms, design).  ``n_jobs`` > 1
     generates the chromosomes in that many forked processes (same files: the
     random streams are per chromosome and replicate); fork before the process
-    has initialised CUDA."""
+    has initialised CUDA.  ``generate=False`` only describes a dataset that an
+    earlier call with the same arguments wrote."""
     import pandas as pd
     rep_names = ['A%d' % (i + 1) for i in range(n_reps // 2)] + \
         ['B%d' % (i + 1) for i in range(n_reps - n_reps // 2)]
@@ -153,7 +154,9 @@ def write_dataset(root, chrom_sizes, n_reps=4, dist_max=200, config=1,
     tasks = [(root, rep_names, ci, chrom, n, n_reps, dist_max, config, amp,
               res_scale, loops, dtype)
              for ci, (chrom, n) in enumerate(chrom_sizes.items())]
-    if n_jobs > 1 and len(tasks) > 1:
+    if not generate:
+        wrote = [loops]
+    elif n_jobs > 1 and len(tasks) > 1:
         import multiprocessing
         # largest chromosomes first: the pool drains evenly
         order = sorted(range(len(tasks)), key=lambda i: -tasks[i][4])

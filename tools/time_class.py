@@ -2,7 +2,7 @@
 per step: SURVEY.md section 8(d) "end-to-end" clock for BASELINE configs[0]
 (chr18 + chr19, mouse-sized, 10 kb, 2-vs-2).
 
-    python tools/time_class.py [workdir] [--chroms=chr18,chr19 | --chroms=all]
+    python tools/time_class.py [workdir] [--chroms=chr18,chr19 | --chroms=all] [--reuse]
 
 ``--chroms=all``: BASELINE configs[1], the whole mouse genome (20 chromosomes,
 48.4 M union pixels, ~2.3 GB of .npz in, ~8.2 GB of .npy out): only the
@@ -34,7 +34,9 @@ def main():
     t0 = time.perf_counter()
     kw = write_dataset(os.path.join(root, 'in'),
                        {c: MM10_10KB[c] for c in chroms}, n_reps=4,
-                       dist_max=200, config=1, n_jobs=os.cpu_count() or 1)
+                       dist_max=200, config=1, n_jobs=os.cpu_count() or 1,
+                       generate='--reuse' not in sys.argv or
+                       not os.path.isdir(os.path.join(root, 'in')))
     t_gen = time.perf_counter() - t0
     out = {}
     for trial in range(0 if genome else 2):   # second pass: page cache and CUDA context warm
