@@ -27,6 +27,7 @@ import json
 import os
 import sys
 import threading
+import time
 from concurrent.futures import ThreadPoolExecutor
 
 import dill as pickle
@@ -408,6 +409,13 @@ class HiC3DeFDR(object):
         except OSError:
             return 1
 
+    def _add_time(self, key, t0):
+        """host seconds since ``t0`` added to ``self.timings[key]`` (where the
+        wall time of a files-in -> files-out run goes); returns now."""
+        now = time.perf_counter()
+        self.timings[key] = self.timings.get(key, 0.0) + now - t0
+        return now
+
     def _io_threads(self, n_threads):
         if n_threads is None or n_threads == 0:
             return 1
@@ -439,9 +447,14 @@ class HiC3DeFDR(object):
         that waits for them and gives (bias_raw, mats, loop_pixels)."""
         bias = [pool.submit(_loadtxt, p.replace('<chrom>', chrom))
                 for p in self.bias_patterns]
-        mats = [pool.submit(
-            lambda p: hostio.load_npz(p).tocsr(), p.replace('<chrom>', chrom))
-            for p in self.raw_npz_patterns]
+        def load_matrix(path):
+            m = hostio.load_npz(path).tocsr()
+            # O(nnz) scan, cached on the matrix: ops.DeviceCSR asks for it on
+            # the main thread
+            m.has_canonical_format
+            return m
+        mats = [pool.submit(load_matrix, p.replace('<chrom>', chrom))
+                for p in self.raw_npz_patterns]
         loops = [pool.submit(load_clusters, pattern.replace('<chrom>', chrom))
                  for pattern in self.loop_patterns.values()] \
             if self.loop_patterns else None
@@ -536,11 +549,14 @@ class HiC3DeFDR(object):
             chroms = self._my_chroms()
             defer, self._defer_writes = self._defer_writes, True
             try:
+                t_wait = time.perf_counter()
                 for c, inputs in self._prefetched_inputs(chroms, n_threads):
+                    self._add_time('prepare/wait_for_files', t_wait)
                     self.prepare_data(chrom=c, norm=norm, n_bins=n_bins,
                                       n_threads=n_threads, verbose=False,
                                       _inputs=inputs)
                     del inputs
+                    t_wait = time.perf_counter()
             finally:
                 self._defer_writes = defer
             if not defer:
@@ -559,8 +575,10 @@ class HiC3DeFDR(object):
             me = hdist.rank()
             mats = staging.shard_rows(mats, int(bounds[me]),
                                       int(bounds[me + 1]))
+        t0 = time.perf_counter()
         csr = ops.DeviceCSR(mats)
         del mats
+        t0 = self._add_time('prepare/upload', t0)
         if self.loop_patterns:
             eprint('  making loop_idx', skip=not verbose)
         eprint('  loading raw data', skip=not verbose)
@@ -574,6 +592,7 @@ class HiC3DeFDR(object):
             self.dist_thresh_max, self.bias_thresh, self.mean_thresh, norm,
             n_bins, loop_pixels)
         del csr
+        t0 = self._add_time('prepare/kernels_and_readbacks', t0)
         eprint('  saving data to disk', skip=not verbose)
         to_save = [(st[k].bool() if k in ('disp_idx', 'loop_idx') else st[k],
                     k, chrom)
@@ -596,6 +615,7 @@ class HiC3DeFDR(object):
             self._save_many(to_save, n_threads)
         st.pop('scaled')
         self._cache[chrom] = st
+        self._add_time('prepare/queue_writes', t0)
 
     # ------------------------------------------------------ estimate_disp
     def estimate_disp(self, estimator='qcml', frac=None, auto_frac_factor=15.,

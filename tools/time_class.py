@@ -55,12 +55,19 @@ def main():
         n_px = sum(len(h.load_data('row', c)) for c in chroms)
         nbytes = sum(os.path.getsize(os.path.join(outdir, f))
                      for f in os.listdir(outdir))
+        times['prepare_host'] = {k: round(v, 3) for k, v in h.timings.items()
+                                 if k.startswith('prepare/')}
         out['trial%d' % trial] = dict(times, union_pixels=n_px,
                                       output_bytes=nbytes,
                                       pixels_per_s=round(n_px / times['total']))
     # the whole pipeline in one call: writers of a step overlap the next step
+    import gc
     import shutil
-    for trial in range(2):
+    threads = [-1]
+    for a in sys.argv[1:]:
+        if a.startswith('--threads='):     # I/O thread settings to compare
+            threads = [int(v) for v in a.split('=', 1)[1].split(',')]
+    for n_threads, trial in [(n, t) for n in threads for t in range(2)]:
         outdir = os.path.join(root, 'out_all')
         shutil.rmtree(outdir, ignore_errors=True)
         h = HiC3DeFDR(outdir=outdir, dist_thresh_max=200, **kw)
@@ -84,8 +91,12 @@ def main():
         h.prepare_data = lambda *a, **k: (
             timed('prepare_data', prepare)(*a, **k) if k.get('chrom') is None
             else prepare(*a, **k))
+        # the wrappers above make the previous instance a reference cycle:
+        # collect it (device cache, writer threads, pinned buffers) now, not
+        # somewhere inside the timed call
+        gc.collect()
         t = time.perf_counter()
-        h.run_to_qvalues()
+        h.run_to_qvalues(n_threads=n_threads)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t
         n_px = sum(len(h.load_data('row', c)) for c in chroms)
@@ -94,11 +105,15 @@ def main():
         in_bytes = sum(os.path.getsize(p.replace('<chrom>', c))
                        for p in kw['raw_npz_patterns'] + kw['bias_patterns']
                        for c in chroms)
-        out['run_to_qvalues_%d' % trial] = dict(
-            total=round(dt, 3), host_steps=host, union_pixels=n_px,
+        key = 'run_to_qvalues_%d' % trial if n_threads == -1 else \
+            'run_to_qvalues_threads%d_%d' % (n_threads, trial)
+        out[key] = dict(
+            total=round(dt, 3), host_steps=host,
+            prepare_host={k: round(v, 3) for k, v in h.timings.items()
+                          if k.startswith('prepare/')}, union_pixels=n_px,
             input_bytes=in_bytes,
             output_bytes=nbytes, pixels_per_s=round(n_px / dt))
-        del h
+        del h, prepare
     out['generate_inputs_s'] = round(t_gen, 1)
     print(json.dumps(out))
 
