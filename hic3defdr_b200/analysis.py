@@ -447,12 +447,17 @@ class HiC3DeFDR(object):
         that waits for them and gives (bias_raw, mats, loop_pixels)."""
         bias = [pool.submit(_loadtxt, p.replace('<chrom>', chrom))
                 for p in self.bias_patterns]
+        device = torch.cuda.current_device() if torch.cuda.is_available() \
+            else None
+
         def load_matrix(path):
             m = hostio.load_npz(path).tocsr()
             # O(nnz) scan, cached on the matrix: ops.DeviceCSR asks for it on
             # the main thread
             m.has_canonical_format
-            return m
+            # page-locked copy (made here, on the I/O thread): the main thread
+            # only queues asynchronous uploads
+            return hostio.pin_csr(m, device)
         mats = [pool.submit(load_matrix, p.replace('<chrom>', chrom))
                 for p in self.raw_npz_patterns]
         loops = [pool.submit(load_clusters, pattern.replace('<chrom>', chrom))

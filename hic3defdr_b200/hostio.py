@@ -118,3 +118,32 @@ def load_npz(path, pool=None):
         return cls((data, offsets), shape=shape)
     data, indices, indptr = parts
     return cls((data, indices, indptr), shape=shape)
+
+
+def pin_csr(m, device=None):
+    """The CSR matrix ``m`` re-based on page-locked host memory: the same
+    matrix (scipy object over numpy views of pinned torch tensors, canonical
+    flag carried over) whose arrays ``ops.DeviceCSR`` uploads with asynchronous
+    copies instead of blocking pageable ones.  The pinned tensors ride along
+    as ``m._h3d_pinned`` (data, indices, indptr).  Returns ``m`` itself when
+    there is no CUDA device or a dtype torch cannot hold."""
+    import torch
+    if not torch.cuda.is_available():
+        return m
+    if device is not None:
+        torch.cuda.set_device(device)      # loader threads start on device 0
+    parts = []
+    try:
+        for a in (m.data, m.indices, m.indptr):
+            a = np.ascontiguousarray(a)
+            dtype = torch.from_numpy(np.empty(0, dtype=a.dtype)).dtype
+            t = torch.empty(a.shape, dtype=dtype, pin_memory=True)
+            np.copyto(t.numpy(), a)
+            parts.append(t)
+    except (TypeError, RuntimeError):
+        return m
+    out = sparse.csr_matrix(tuple(t.numpy() for t in parts), shape=m.shape)
+    if m.has_canonical_format:
+        out.has_canonical_format = True
+    out._h3d_pinned = tuple(parts)
+    return out

@@ -154,11 +154,16 @@ class DeviceCSR(object):
         self.indptr, self.indices, self.data = [], [], []
         self.n_bins = mats[0].shape[0]
         dtypes, is64 = set(), set()
+        pinned = []
         for m in mats:
-            m = sparse.csr_matrix(m)
+            if not (sparse.issparse(m) and m.format == 'csr'):
+                m = sparse.csr_matrix(m)
+            # (data, indices, indptr) in page-locked memory, hostio.pin_csr
+            pin = getattr(m, '_h3d_pinned', None)
             if not m.has_canonical_format:
                 m = m.copy()
                 m.sum_duplicates()
+                pin = None
             dt = m.data.dtype
             if dt not in _DTYPES:
                 dt = np.dtype(np.float64) if dt.kind == 'f' else \
@@ -168,12 +173,25 @@ class DeviceCSR(object):
             self.indptr.append(m.indptr)
             self.indices.append(m.indices.astype(np.int32, copy=False))
             self.data.append(m.data)
+            pinned.append(pin or (None, None, None))
         self.dtype = dtypes.pop() if len(dtypes) == 1 else np.dtype(np.float64)
         self.is64 = int(any(is64))
         ip_t = np.int64 if self.is64 else np.int32
-        self.indptr = [dev(a.astype(ip_t, copy=False)) for a in self.indptr]
-        self.indices = [dev(a) for a in self.indices]
-        self.data = [dev(a.astype(self.dtype, copy=False)) for a in self.data]
+
+        def upload(a, t, dtype):
+            # the pinned tensor holds exactly this array: asynchronous copy on
+            # the current stream (the host allocator keeps the block until the
+            # copy is done); anything else: blocking copy of the array
+            if t is not None and a.dtype == dtype and a.size == t.numel() \
+                    and a.size and a.ctypes.data == t.data_ptr():
+                return t.cuda(non_blocking=True)
+            return dev(a.astype(dtype, copy=False))
+        self.indptr = [upload(a, p[2], ip_t)
+                       for a, p in zip(self.indptr, pinned)]
+        self.indices = [upload(a, p[1], np.int32)
+                        for a, p in zip(self.indices, pinned)]
+        self.data = [upload(a, p[0], self.dtype)
+                     for a, p in zip(self.data, pinned)]
         self.nnz = sum(int(d.numel()) for d in self.data)
 
     def pointer_arrays(self):
