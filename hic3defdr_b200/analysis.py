@@ -447,17 +447,22 @@ class HiC3DeFDR(object):
         that waits for them and gives (bias_raw, mats, loop_pixels)."""
         bias = [pool.submit(_loadtxt, p.replace('<chrom>', chrom))
                 for p in self.bias_patterns]
-        device = torch.cuda.current_device() if torch.cuda.is_available() \
-            else None
+        # H3D_PIN_INPUTS=1: the I/O threads also copy the matrices to
+        # page-locked memory and the main thread only queues asynchronous
+        # uploads.  Worth it for a process that makes many runs (genome scale,
+        # B200: 0.78 -> 0.63 s per run); off by default because the first run
+        # of a process pays ~3 s for the page-locked allocations.
+        device = None
+        if os.environ.get('H3D_PIN_INPUTS', '0') not in ('', '0') and \
+                torch.cuda.is_available():
+            device = torch.cuda.current_device()
 
         def load_matrix(path):
             m = hostio.load_npz(path).tocsr()
             # O(nnz) scan, cached on the matrix: ops.DeviceCSR asks for it on
             # the main thread
             m.has_canonical_format
-            # page-locked copy (made here, on the I/O thread): the main thread
-            # only queues asynchronous uploads
-            return hostio.pin_csr(m, device)
+            return m if device is None else hostio.pin_csr(m, device)
         mats = [pool.submit(load_matrix, p.replace('<chrom>', chrom))
                 for p in self.raw_npz_patterns]
         loops = [pool.submit(load_clusters, pattern.replace('<chrom>', chrom))
