@@ -247,76 +247,93 @@ class HiC3DeFDR(object):
                                         self.bias_thresh)
         return c['bias']
 
+    # which pixel set the rows of a per-pixel output are aligned with
+    # (docs/data_layout.md of the reference): the union pixels, the tested
+    # ones (row[disp_idx]) or the loop pixels among those
+    _ALIGNED_WITH = dict(
+        [(n, 'union') for n in ('raw', 'size_factors', 'scaled', 'disp_idx')] +
+        [(n, 'tested') for n in ('loop_idx', 'disp', 'mu_hat_null',
+                                 'mu_hat_alt', 'llr', 'pvalues')] +
+        [('qvalues', 'loops')])
+    _NOT_PER_PIXEL = ('row', 'col', 'bias', 'cov_per_bin', 'disp_per_bin')
+
+    def _data_file(self, name, chrom=None):
+        return '%s/%s.npy' % (self.outdir, name) if chrom is None else \
+            '%s/%s_%s.npy' % (self.outdir, name, chrom)
+
+    def _read_rows(self, path, keep=None):
+        """the rows ``keep`` (boolean mask) of a saved array, all if None; a
+        masked read maps the file instead of loading it whole"""
+        if keep is None:
+            return np.load(path)
+        return np.load(path, mmap_mode='r')[keep]
+
+    def _pixel_coordinates(self, name, chrom):
+        """(row, col) of the pixels the rows of ``name`` belong to."""
+        level = self._ALIGNED_WITH[name]
+        keep = None
+        if level != 'union':
+            keep = self.load_data('disp_idx', chrom)
+            if level == 'loops':
+                keep = self._chain_masks(keep,
+                                         self.load_data('loop_idx', chrom))
+        return (self._read_rows(self._data_file('row', chrom), keep),
+                self._read_rows(self._data_file('col', chrom), keep))
+
+    @staticmethod
+    def _chain_masks(outer, inner):
+        """mask over everything that selects the ``inner``-selected ones of
+        the ``outer``-selected entries (``x[outer][inner] == x[chained]``)"""
+        chained = np.zeros(len(outer), dtype=bool)
+        chained[np.flatnonzero(outer)[inner]] = True
+        return chained
+
     def load_data(self, name, chrom=None, idx=None, rep=None, cond=None,
                   coo=False):
-        """analysis/core.py:62-195 (same semantics, numpy in / out)."""
+        """The reference's loader (analysis/core.py:62-195): one saved array,
+        whole (``chrom=None``), of one chromosome, or of all of them
+        concatenated (``chrom='all'``: returns (data, offsets)); ``idx``: a
+        boolean row mask or a (mask, mask-of-the-selected) pair; ``rep`` /
+        ``cond``: one column by replicate / condition name; ``coo=True``:
+        (row, col, data) of one chromosome."""
         self._flush_writes()
         if name == 'loop_idx' and self.loop_patterns is None and idx is None \
                 and chrom != 'all':
-            disp_idx = self.load_data('disp_idx', chrom)
-            return np.ones(disp_idx.sum(), dtype=bool)
-        col_idx = self.design.index.tolist().index(rep) if rep is not None \
-            else self.design.columns.tolist().index(cond) \
-            if cond is not None else None
+            # no loops given: every tested pixel counts as one
+            return np.ones(int(self.load_data('disp_idx', chrom).sum()),
+                           dtype=bool)
+        column = None
+        if rep is not None:
+            column = list(self.design.index).index(rep)
+        elif cond is not None:
+            column = list(self.design.columns).index(cond)
+        pick = (lambda a: a) if column is None else (lambda a: a[:, column])
         if coo:
             if chrom == 'all' or idx is not None:
                 raise ValueError("cannot pass coo=True with chrom='all' or idx")
-            if name in ['row', 'col', 'bias', 'cov_per_bin', 'disp_per_bin']:
+            if name in self._NOT_PER_PIXEL:
                 raise ValueError('data with name %s cannot be loaded as COO'
                                  % name)
-            if name in ['raw', 'size_factors', 'scaled', 'disp_idx']:
-                row = self.load_data('row', chrom)
-                col = self.load_data('col', chrom)
-            elif name in ['loop_idx', 'disp', 'mu_hat_null', 'mu_hat_alt',
-                          'llr', 'pvalues']:
-                disp_idx = self.load_data('disp_idx', chrom)
-                row = self.load_data('row', chrom, idx=disp_idx)
-                col = self.load_data('col', chrom, idx=disp_idx)
-            elif name in ['qvalues']:
-                disp_idx = self.load_data('disp_idx', chrom)
-                loop_idx = self.load_data('loop_idx', chrom)
-                row = self.load_data('row', chrom, idx=(disp_idx, loop_idx))
-                col = self.load_data('col', chrom, idx=(disp_idx, loop_idx))
-            else:
+            if name not in self._ALIGNED_WITH:
                 raise ValueError('data name %s not recognized' % name)
-            data = self.load_data(name, chrom)
-            if col_idx is not None:
-                return row, col, data[:, col_idx]
-            return row, col, data
-        if type(idx) == tuple:
-            big_idx, small_idx = idx
-            big_idx = big_idx.copy()
-            big_idx[np.where(big_idx)[0][~small_idx]] = False
-            idx = big_idx
-        if chrom is None:
-            fname = '%s/%s.npy' % (self.outdir, name)
-        elif chrom != 'all':
-            fname = '%s/%s_%s.npy' % (self.outdir, name, chrom)
-        else:
-            fname = None
-        if fname is not None:
-            if idx is None:
-                data = np.load(fname)
-                return data[:, col_idx] if col_idx is not None else data
-            data = np.load(fname, mmap_mode='r')
-            return data[idx, col_idx] if col_idx is not None else data[idx]
-        idx_offset, offset, offsets, all_data = 0, 0, [0], []
-        for chrom in self.chroms:
-            fname = '%s/%s_%s.npy' % (self.outdir, name, chrom)
-            if idx is not None:
-                data = np.load(fname, mmap_mode='r')
-                full = data.shape[0]
-                data = data[idx[idx_offset:idx_offset + full]]
-                idx_offset += full
+            row, col = self._pixel_coordinates(name, chrom)
+            return row, col, pick(self.load_data(name, chrom))
+        keep = self._chain_masks(*idx) if type(idx) == tuple else idx
+        if chrom != 'all':
+            return pick(self._read_rows(self._data_file(name, chrom), keep))
+        # genome-wide: ``keep`` runs over the concatenation of the chromosomes
+        pieces, start = [], 0
+        for c in self.chroms:
+            path = self._data_file(name, c)
+            if keep is None:
+                pieces.append(np.load(path))
             else:
-                data = np.load(fname)
-            offset += data.shape[0]
-            offsets.append(offset)
-            all_data.append(data)
-        all_data = np.concatenate(all_data)
-        if col_idx is not None:
-            return all_data[:, col_idx], np.array(offsets)
-        return all_data, np.array(offsets)
+                rows = np.load(path, mmap_mode='r')
+                pieces.append(rows[keep[start:start + rows.shape[0]]])
+                start += rows.shape[0]
+        offsets = np.concatenate(
+            [[0], np.cumsum([p.shape[0] for p in pieces])]).astype(np.int64)
+        return pick(np.concatenate(pieces)), offsets
 
     def save_data(self, data, name, chrom=None):
         """analysis/core.py:197-218."""

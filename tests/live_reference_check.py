@@ -47,6 +47,111 @@ VARIANTS = {
 }
 
 
+def compare_loaders(ref, outdir, chroms, has_loops):
+    """The drop-in class opened on the directory the REFERENCE wrote
+    (``HiC3DeFDR.load``: its pickle, its files): ``load_data`` must return what
+    the reference's own ``load_data`` returns (analysis/core.py:62-195) for
+    every way of calling it -- per chromosome, genome-wide with offsets,
+    masks, chained masks, one column by replicate / condition, COO triples,
+    and the same exceptions."""
+    from hic3defdr_b200 import HiC3DeFDR
+    ours = HiC3DeFDR.load(outdir)
+    assert ours.chroms == ref.chroms and ours.design.equals(ref.design)
+    rng = np.random.default_rng(5)
+    n = [0]
+
+    def same(a, b):
+        if isinstance(b, tuple):
+            assert isinstance(a, tuple) and len(a) == len(b)
+            for x, y in zip(a, b):
+                same(x, y)
+            return
+        a, b = np.asarray(a), np.asarray(b)
+        assert a.dtype == b.dtype and a.shape == b.shape, (a.dtype, b.dtype,
+                                                           a.shape, b.shape)
+        assert np.array_equal(a, b, equal_nan=a.dtype.kind == 'f')
+
+    def check(*args, **kw):
+        try:
+            want = ref.load_data(*args, **kw)
+        except Exception as e:            # same failure, same type
+            try:
+                ours.load_data(*args, **kw)
+            except Exception as e2:
+                assert type(e2) is type(e), (args, kw, e, e2)
+                n[0] += 1
+                return
+            raise AssertionError('reference raised %r, we did not: %r %r'
+                                 % (e, args, kw))
+        same(ours.load_data(*args, **kw), want)
+        n[0] += 1
+
+    rep, cond = ref.design.index[1], ref.design.columns[1]
+    union = ['row', 'col', 'raw', 'size_factors', 'scaled', 'disp_idx']
+    tested = ['disp', 'pvalues', 'llr', 'mu_hat_null', 'mu_hat_alt'] + \
+        (['loop_idx'] if has_loops else [])
+    check('disp_per_dist')
+    for name in union + tested + ['qvalues']:
+        check(name, 'all')
+        for c in chroms:
+            check(name, c)
+            # (qvalues as COO without loops runs into the reference's broken
+            # loop_idx shortcut, see below)
+            if name not in ('row', 'col') and (has_loops or name != 'qvalues'):
+                check(name, c, coo=True)
+        if name in ('row', 'col'):
+            check(name, chroms[0], coo=True)      # ValueError
+    for name in ('raw', 'scaled', 'size_factors'):
+        check(name, chroms[0], rep=rep)
+        check(name, 'all', rep=rep)
+        check(name, chroms[-1], rep=rep, coo=True)
+    for name in ('disp', 'mu_hat_alt'):
+        check(name, chroms[0], cond=cond)
+        check(name, 'all', cond=cond)
+        check(name, chroms[0], cond=cond, coo=True)
+    # masks: per chromosome, genome-wide, chained
+    disp_all, offs = ref.load_data('disp_idx', 'all')
+    for c in chroms:
+        di = ref.load_data('disp_idx', c)
+        check('row', c, idx=di)
+        check('raw', c, idx=di, rep=rep)
+        sub = rng.random(int(di.sum())) < 0.4
+        check('col', c, idx=(di, sub))
+        check('scaled', c, idx=(di, sub), rep=rep)
+        check('pvalues', c, idx=sub)
+    check('row', 'all', idx=disp_all)
+    check('raw', 'all', idx=disp_all, rep=rep)
+    sub = rng.random(int(disp_all.sum())) < 0.3
+    check('col', 'all', idx=(disp_all, sub))
+    check('llr', 'all', idx=sub)
+    check('disp', 'all', idx=sub, cond=cond)
+    if has_loops:
+        loop_all, _ = ref.load_data('loop_idx', 'all')
+        check('row', 'all', idx=(disp_all, loop_all))
+        for c in chroms:
+            check('row', c, idx=(ref.load_data('disp_idx', c),
+                                 ref.load_data('loop_idx', c)))
+    # failures
+    check('raw', 'all', coo=True)
+    check('raw', chroms[0], idx=ref.load_data('disp_idx', chroms[0]), coo=True)
+    check('bias', chroms[0], coo=True)
+    check('no_such_name', chroms[0], coo=True)
+    check('no_such_name', chroms[0])
+    check('raw', chroms[0], rep='no_such_rep')
+    if not has_loops:
+        # the reference's shortcut for runs without loops calls a function
+        # that does not exist (core.py:107 ``np.load_data``); the intended
+        # result is one True per tested pixel
+        for c in chroms:
+            got = ours.load_data('loop_idx', c)
+            assert got.dtype == bool and got.all() and \
+                len(got) == int(ref.load_data('disp_idx', c).sum())
+            same(ours.load_data('qvalues', c, coo=True)[:2],
+                 (ref.load_data('row', c, idx=ref.load_data('disp_idx', c)),
+                  ref.load_data('col', c, idx=ref.load_data('disp_idx', c))))
+    return n[0]
+
+
 def main(variant):
     from oracle import pipeline as op
     from oracle import refrun
@@ -104,9 +209,11 @@ def main(variant):
         for ci, cond in enumerate(kw['design'].columns):
             assert np.array_equal(op.eval_trend(res['fits'][ci], xs),
                                   h.load_disp_fn(cond)(xs.copy()), equal_nan=True)
+        n_loader = compare_loaders(h, outdir, list(sizes), bool(loops))
         n_px = sum(len(st['row']) for st in res['chroms'])
         print('live reference check %s: ok (%d arrays bit-identical, %d union '
-              'pixels)' % (variant, n_checked + 1, n_px))
+              'pixels, %d load_data calls equal)'
+              % (variant, n_checked + 1, n_px, n_loader))
     finally:
         shutil.rmtree(root, ignore_errors=True)
 
