@@ -152,6 +152,39 @@ def compare_loaders(ref, outdir, chroms, has_loops):
     return n[0]
 
 
+def reference_opens_our_directory(Ref, ref, kw, res, dist_max, root):
+    """The other direction of the file contract: a directory made by the
+    drop-in class (its pickle, its ``disp_fn_<cond>.pickle``) opens in the
+    REFERENCE class (analysis/core.py:15-33, 220-237), and the product's
+    dispersion callable (hic3defdr_b200/trend.py::DispersionTrend, here built
+    from the oracle's fit = the reference's lowess curve bit for bit) evaluates
+    to what the reference's own pickled closure gives, in and out of range."""
+    from hic3defdr_b200 import HiC3DeFDR
+    from hic3defdr_b200.trend import DispersionTrend
+    outdir = os.path.join(root, 'ours')
+    ours = HiC3DeFDR(outdir=outdir, dist_thresh_max=dist_max, **kw)
+    xs = np.concatenate([np.arange(dist_max + 1), [dist_max + 7]]), \
+        np.array([-2.0, 0.0, 0.5, 3.99, 4.0, 4.5, 7.25, dist_max - 0.5,
+                  dist_max + 3.5])
+    for ci, cond in enumerate(ours.design.columns):
+        fit = res['fits'][ci]
+        ours.save_disp_fn(cond, DispersionTrend(
+            fit['x'], fit['y'], fit['inc'], fit['cx'], fit['cy'], fit['frac'],
+            fit['left_boundary'], None, weighted=fit['weighted']))
+    theirs = Ref.load(outdir)
+    for attr in ('raw_npz_patterns', 'bias_patterns', 'chroms',
+                 'dist_thresh_min', 'dist_thresh_max', 'bias_thresh',
+                 'mean_thresh', 'loop_patterns', 'res'):
+        assert getattr(theirs, attr) == getattr(ref, attr), attr
+    assert theirs.design.equals(ref.design)
+    for cond in ours.design.columns:
+        fn, want = theirs.load_disp_fn(cond), ref.load_disp_fn(cond)
+        for x in xs:               # integer and float arguments
+            got = fn(x.copy())
+            assert got.dtype == np.float64 and \
+                np.array_equal(got, want(x.copy()), equal_nan=True), cond
+
+
 def main(variant):
     from oracle import pipeline as op
     from oracle import refrun
@@ -210,6 +243,7 @@ def main(variant):
             assert np.array_equal(op.eval_trend(res['fits'][ci], xs),
                                   h.load_disp_fn(cond)(xs.copy()), equal_nan=True)
         n_loader = compare_loaders(h, outdir, list(sizes), bool(loops))
+        reference_opens_our_directory(Ref, h, kw, res, dist_max, root)
         n_px = sum(len(st['row']) for st in res['chroms'])
         print('live reference check %s: ok (%d arrays bit-identical, %d union '
               'pixels, %d load_data calls equal)'
