@@ -74,3 +74,28 @@ def test_prefetched_inputs_surface_a_missing_file(tmp_path):
     assert next(it)[0] == 'chr1'
     with pytest.raises(OSError):
         next(it)
+
+
+def test_chunked_npy_writer_equals_np_save(tmp_path):
+    """The staged writer streams an array to disk chunk by chunk
+    (``write_npy_chunks``): the file must be np.save's, byte for byte, for
+    every dtype / shape the pipeline writes (int32 row, int64 (N, R) raw, bool
+    masks, float64 vectors and matrices, empty arrays, 0-d)."""
+    from hic3defdr_b200.analysis import _AsyncWriter
+    rng = np.random.default_rng(1)
+    arrays = [rng.random((1000, 4)), rng.integers(0, 9, 5000).astype(np.int32),
+              rng.random(7) > 0.5, np.zeros((0, 2)), np.zeros(0, dtype=bool),
+              rng.integers(0, 2 ** 40, (33, 2)), np.float64(3.5) * np.ones(()),
+              rng.random((5, 3, 2)).astype(np.float32)]
+    for i, a in enumerate(arrays):
+        a = np.ascontiguousarray(a)
+        ref, got = str(tmp_path / 'ref.npy'), str(tmp_path / 'got.npy')
+        np.save(ref, a)
+        raw = a.tobytes()
+        for step in (1 << 20, 997):
+            _AsyncWriter.write_npy_chunks(
+                got, a.dtype, a.shape,
+                (raw[j:j + step] for j in range(0, len(raw), step)))
+            assert open(got, 'rb').read() == open(ref, 'rb').read(), (i, step)
+            back = np.load(got)
+            assert back.dtype == a.dtype and np.array_equal(back, a)
