@@ -310,3 +310,38 @@ def test_far_tail_quantile_map_is_exact(L):
           % (got[0], err_ours, ref, err_ref))
     assert err_ours < 1e-13
     assert 1e-9 < err_ref < 1e-7           # the reference's own error
+
+
+@pytest.mark.parametrize('df', [1, 2, 3])
+def test_chi2_survival_function_vs_scipy(L, df):
+    """chi2_sf (the LRT's p-value, util/lrt.py:47: ``stats.chi2(df).sf``) over
+    15 decades of the statistic, df = C - 1 for 2 to 4 conditions: 1e-12
+    relative down to p = 1e-290 (the argument of exp(-x/2) carries
+    |x| 1e-16 either way), nothing above the last few subnormals where scipy
+    underflows to zero, sf(0) = 1, sf(x >= 1500) = sf(inf) = 0."""
+    import scipy.stats as st
+    rng = np.random.default_rng(df)
+    x = np.concatenate([10 ** rng.uniform(-14, 3.3, 100000),
+                        [0.0, 1e-300, 1e-8, 745.0, 1400.0, 1500.0, 5000.0,
+                         np.inf]])
+    out = np.zeros_like(x)
+    L.hc_chi2_sf(P(x), len(x), df, P(out))
+    want = st.chi2.sf(x, df)
+    m = want > 1e-290
+    assert (np.abs(out[m] - want[m]) / want[m]).max() < 1e-12
+    assert (out[want == 0] <= 1e-320).all() and (out[x == 0] == 1).all()
+    assert (out[x >= 1500.0] == 0).all()
+    sub = ~m & (want > 0)                     # subnormal results: absolute
+    assert (np.abs(out[sub] - want[sub]) <= 1e-12 * want[sub] + 1e-320).all()
+
+
+def test_lgamma_pos_vs_scipy(L):
+    """lgamma_pos (constants of the conditional likelihood, lgamma(n r) and
+    lgamma(r), util/dispersion.py:72-75) for 1e-3 <= x <= 1e7"""
+    rng = np.random.default_rng(4)
+    xs = np.concatenate([10 ** rng.uniform(-3, 7, 100000),
+                         [1.0, 2.0, 0.5, 9.999999, 10.0, 10.000001]])
+    out = np.zeros_like(xs)
+    L.hc_lgamma_pos(P(xs), len(xs), P(out))
+    want = sp.gammaln(xs)
+    assert (np.abs(out - want) / np.maximum(np.abs(want), 1.0)).max() < 3e-14
